@@ -1,0 +1,112 @@
+/*
+ * pcl.h -- C ABI of libpcl.so, the B200 (sm_100a) batched Polar / LDPC decoder.
+ *
+ * The reference (B1ear/PolarCode_and_LDPC) is pure Python and has no FFI layer;
+ * its boundary for the decode hot path is the Python class API.  Each entry
+ * point below names the reference interface it stands behind (paths relative to
+ * the reference root).  The Python drop-in classes in polarcode_and_ldpc_b200/
+ * bind these with ctypes (see INTEGRATION.md for the stub a reference
+ * maintainer would add).
+ *
+ * Conventions: plain pointers and sizes, no torch types.  *_dev pointers are
+ * device pointers borrowed for the duration of the call (never freed here);
+ * *_host pointers are host memory (pinned memory makes the copies asynchronous).
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Every
+ * function returns 0 on success, a PCL_E* code otherwise; pcl_last_error() gives
+ * the text.  A handle may be used from one stream at a time.  There is no CPU
+ * fallback: without a CUDA device every compute call fails with PCL_ECUDA.
+ */
+#ifndef PCL_H
+#define PCL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_OK 0
+#define PCL_EINVAL 1      /* bad argument (AssertionError on the Python side) */
+#define PCL_ECUDA 2       /* CUDA runtime error / no device */
+#define PCL_EUNSUPPORTED 3
+#define PCL_EDEGREE1 4    /* Min-Sum on a degree-1 check: reference raises ValueError */
+
+#define PCL_F32 0         /* production compute type */
+#define PCL_F64 1         /* validation build: bit-exact decoded bits vs the reference */
+
+#define PCL_LDPC_BP 0     /* BPDecoder  (src/ldpc/decoder.py:11)  */
+#define PCL_LDPC_MS 1     /* MSDecoder  (src/ldpc/decoder.py:208) */
+
+typedef struct pcl_polar pcl_polar_t;
+typedef struct pcl_ldpc pcl_ldpc_t;
+
+int pcl_version(void);
+const char* pcl_last_error(void);
+int pcl_device_count(void);
+
+/*
+ * SCDecoder.__init__ (src/polar/decoder.py:16-36) / SCLDecoder.__init__ (:191-223).
+ * frozen_mask[l] != 0 marks reference bit index l as frozen (N entries); K must
+ * equal the number of zeros.  list_size 1 with want_metric 0 is the SC decoder.
+ * crc_len 0 disables CRC-aided selection (the reference never applies it,
+ * decoder.py:259); otherwise crc_poly/crc_len follow src/polar/utils.py:128-163.
+ */
+int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
+                     int crc_len, uint32_t crc_poly, int dtype);
+void pcl_polar_destroy(pcl_polar_t* h);
+
+/*
+ * SCDecoder.decode (src/polar/decoder.py:38-71) / SCLDecoder.decode (:225-262) over
+ * F frames.  llr_dev: [F][N] in the handle's dtype.  bits_dev: [F][K] bytes, the
+ * info bits in ascending reference index (what decode() returns).  Optional
+ * outputs (NULL to skip): pm_dev [F][list_size] doubles = SCLDecoder.path_metrics;
+ * leaf_dev [F][N][LP] (dtype) + parent_dev [F][N][LP] bytes = per-step leaf LLR
+ * and survivor parent of every list slot (LP = list_size rounded up to a power of
+ * two, pcl_polar_lp()), from which the host rebuilds L_paths[best, :, n].
+ */
+int pcl_polar_decode_batch(pcl_polar_t* h, const void* llr_dev, int64_t F, uint8_t* bits_dev,
+                           double* pm_dev, void* leaf_dev, uint8_t* parent_dev, void* stream);
+
+/* Same call with HOST buffers: chunks the batch, overlaps H2D / decode / D2H. */
+int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
+                          void* stream);
+int pcl_polar_lp(const pcl_polar_t* h);
+/* Launch geometry of the last decode (for gpu_launches / occupancy reporting). */
+int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels);
+
+/*
+ * BPDecoder.__init__ / MSDecoder.__init__ + _build_tanner_graph
+ * (src/ldpc/decoder.py:18-60, :215-255).  H_dense: m*n row-major bytes; entries
+ * equal to 1 are edges.  normalization is MSDecoder's factor (ignored for BP).
+ */
+int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H_dense, int mode,
+                    double normalization, int max_iter, int early_stop, int dtype);
+void pcl_ldpc_destroy(pcl_ldpc_t* h);
+
+/*
+ * BPDecoder.decode (src/ldpc/decoder.py:124-202) / MSDecoder.decode (:289-352) over
+ * F frames.  llr_dev [F][n] (dtype); bits_dev [F][n] bytes (whole codeword, as the
+ * reference returns); optional iters_dev [F] int32 (return_iterations=True) and
+ * total_dev [F][n] (dtype) = total LLRs of the last executed iteration.
+ */
+int pcl_ldpc_decode_batch(pcl_ldpc_t* h, const void* llr_dev, int64_t F, uint8_t* bits_dev,
+                          int32_t* iters_dev, void* total_dev, void* stream);
+int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
+                         int32_t* iters_host, void* stream);
+int pcl_ldpc_num_edges(const pcl_ldpc_t* h);
+int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, int* smem_bytes);
+
+/*
+ * np.sum(message != decoded) loops of the callers (benchmarks/test_snr_curves.py:
+ * 133-138).  Adds to counters_dev[4] (uint64): bit errors, frame errors, frames,
+ * bits compared.  Rows are `width` bytes; only the first `ncmp` bytes of each row
+ * are compared (LDPC callers compare decoded[:k]).  The counter tensor is what the
+ * one NCCL allreduce of a multi-GPU sweep reduces.
+ */
+int pcl_count_errors(const uint8_t* bits_dev, const uint8_t* ref_dev, int64_t F, int width, int ncmp,
+                     unsigned long long* counters_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCL_H */

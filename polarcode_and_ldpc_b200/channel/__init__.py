@@ -1,0 +1,1 @@
+from .awgn import AWGNChannel                 # noqa: F401

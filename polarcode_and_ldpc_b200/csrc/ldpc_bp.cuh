@@ -1,0 +1,278 @@
+// ldpc_bp.cuh -- batched flooding BP / Min-Sum LDPC decoder, one warp per frame.
+//
+// Replaces BPDecoder.decode (/root/reference/src/ldpc/decoder.py:124-202, check
+// rule :62-96, variable rule :98-122) and MSDecoder.decode (:289-352, check rule
+// :257-287) for a whole batch, with the reference's schedule: all checks, then all
+// variables, hard decision total <= 0, syndrome early stop.
+//
+// Layout.  Edges are enumerated check-major (row-major scan of H == 1), which is
+// exactly check_neighbors[c] ascending (decoder.py:43-47); `vperm` lists the same
+// edge ids variable-major with checks ascending (var_neighbors[v]).  A frame's E
+// edge messages live in ONE shared-memory array for the whole decode: the check
+// pass overwrites v2c[e] with c2v[e] in place (a check owns its contiguous edge
+// run), the variable pass gathers through vperm and overwrites c2v[e] with v2c[e].
+// HBM sees only the n channel LLRs in and n hard bits out per frame; the Tanner
+// tables are shared by every frame and stay in L1/L2.
+//
+// fp64 build: the reference's arithmetic and association order exactly
+// (tanh -> clip -> left-to-right leave-one-out product -> clip -> 2 atanh;
+// numpy's pairwise np.sum order for the variable sum).
+// fp32 build: same schedule, but the check rule carries w = 1 - |tanh(x/2)| next
+// to t so that messages saturating towards +-1 keep full relative precision
+// (the 0.999999 clip sits where d atanh/dp ~ 5e5; a 1-ulp fp32 error in p would
+// be a 4e-3 relative error in the outgoing LLR).
+#pragma once
+#include "pcl_common.cuh"
+
+struct LdpcLayout {
+    int m, n, E;
+    int max_iter, early_stop;
+    int nhw;                    // hard-decision words = ceil(n / 32)
+    int off_msg, off_llr, off_hard, warp_bytes;
+};
+
+template <typename real>
+struct LdpcParams {
+    LdpcLayout lay;
+    const real* llr;            // [F][n]
+    uint8_t* bits;              // [F][n]
+    int32_t* iters;             // [F] or null
+    real* total;                // [F][n] or null
+    const int32_t* cptr;        // [m+1] edge offsets per check
+    const uint16_t* col;        // [E] variable of edge e
+    const int32_t* vptr;        // [n+1]
+    const uint16_t* vperm;      // [E] edge ids, variable-major
+    unsigned long long* next;   // dynamic frame counter
+    int64_t F;
+    real norm;                  // Min-Sum normalisation
+};
+
+template <typename real> struct ldpc_const;
+template <> struct ldpc_const<float> {
+    static PCL_DEVICE float clipv() { return 0.999999f; }
+    static PCL_DEVICE float wmin() { return 1e-6f; }
+};
+template <> struct ldpc_const<double> {
+    static PCL_DEVICE double clipv() { return 0.999999; }
+    static PCL_DEVICE double wmin() { return 1e-6; }
+};
+
+// ---- check node, reference arithmetic (decoder.py:62-96) -----------------------
+template <int DMAX>
+PCL_DEVICE void cn_bp_exact(double* msg, int d)
+{
+    double t[DMAX];
+#pragma unroll
+    for (int j = 0; j < DMAX; j++) {
+        if (j < d) {
+            double v = tanh(msg[j] / 2.0);
+            v = fmin(fmax(v, -0.999999), 0.999999);
+            t[j] = v;
+        } else {
+            t[j] = 1.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+        if (i < d) {
+            double pr = 1.0;
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < DMAX; j++) {
+                if (j < d && j != i) {
+                    if (first) { pr = t[j]; first = false; } else pr = pr * t[j];
+                }
+            }
+            pr = fmin(fmax(pr, -0.999999), 0.999999);
+            double o = 2.0 * atanh(pr);
+            if (o != o) o = 0.0;                               // np.nan_to_num, :94
+            msg[i] = o;
+        }
+    }
+}
+
+// ---- check node, fp32 production rule (t and w = 1 - |t| side by side) ---------
+template <int DMAX>
+PCL_DEVICE void cn_bp_f32(float* msg, int d)
+{
+    float t[DMAX], w[DMAX];
+#pragma unroll
+    for (int j = 0; j < DMAX; j++) {
+        if (j < d) {
+            const float x = msg[j];
+            float tv = tanhf(0.5f * x);
+            tv = fminf(fmaxf(tv, -0.999999f), 0.999999f);
+            const float u = expf(-fabsf(x));
+            float wv = (2.0f * u) / (1.0f + u);                // 1 - tanh(|x|/2)
+            t[j] = tv;
+            w[j] = fmaxf(wv, 1e-6f);
+        } else {
+            t[j] = 1.0f;
+            w[j] = 0.0f;
+        }
+    }
+    // suffix products, then a running prefix
+    float st[DMAX + 1], sq[DMAX + 1];
+    st[DMAX] = 1.0f;
+    sq[DMAX] = 0.0f;
+#pragma unroll
+    for (int j = DMAX - 1; j >= 0; j--) {
+        st[j] = st[j + 1] * t[j];
+        sq[j] = fmaf(-sq[j + 1], w[j], sq[j + 1] + w[j]);      // 1 - (1-a)(1-b)
+    }
+    float pt = 1.0f, pq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+        if (i < d) {
+            const float pr = pt * st[i + 1];
+            float q = fmaf(-pq, sq[i + 1], pq + sq[i + 1]);
+            float o;
+            if (q < 0.25f) {
+                q = fmaxf(q, 1e-6f);                            // |p| <= 0.999999
+                const float mag = logf((2.0f - q) / q);         // 2 atanh(1 - q)
+                o = (pr < 0.0f) ? -mag : mag;
+            } else {
+                o = 2.0f * atanhf(pr);
+            }
+            msg[i] = o;
+        }
+        pt = pt * t[i];
+        pq = fmaf(-pq, w[i], pq + w[i]);
+    }
+}
+
+// ---- check node, Min-Sum (decoder.py:257-287), any degree, in place -------------
+template <typename real>
+PCL_DEVICE void cn_ms(real* msg, int d, real norm)
+{
+    real m1 = pcl_math<real>::inf(), m2 = pcl_math<real>::inf();
+    int i1 = -1, nneg = 0, nzero = 0;
+    for (int j = 0; j < d; j++) {
+        const real x = msg[j];
+        const real a = fabs(x);
+        if (a < m1) { m2 = m1; m1 = a; i1 = j; } else if (a < m2) { m2 = a; }
+        nneg += (x < (real)0);
+        nzero += (x == (real)0);
+    }
+    for (int i = 0; i < d; i++) {
+        const real x = msg[i];
+        const real mn = (i == i1) ? m2 : m1;
+        const int zeros_other = nzero - (x == (real)0);
+        const int neg_other = nneg - (x < (real)0);
+        real sp = (zeros_other > 0) ? (real)0 : ((neg_other & 1) ? (real)-1 : (real)1);
+        msg[i] = sp * mn * norm;                                // :285
+    }
+}
+
+// numpy add.reduce association order (pairwise_sum) over gathered messages
+template <typename real>
+PCL_DEVICE real vn_sum_np(const real* msg, const uint16_t* ed, int d)
+{
+    if (d < 8) {
+        real r = (real)0;
+        for (int j = 0; j < d; j++) r += msg[ed[j]];
+        return r;
+    }
+    real r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = msg[ed[j]];
+    int i = 8;
+    for (; i < d - (d % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] += msg[ed[i + j]];
+    }
+    real res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < d; i++) res += msg[ed[i]];
+    return res;
+}
+
+template <typename real, int MODE, int DMAX>
+__global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
+{
+    const LdpcLayout& Y = P.lay;
+    const int m = Y.m, n = Y.n, E = Y.E;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* wsm = pcl_dyn_smem() + (size_t)warp * Y.warp_bytes;
+    real* msg = (real*)(wsm + Y.off_msg);
+    real* sllr = (real*)(wsm + Y.off_llr);
+    uint32_t* hard = (uint32_t*)(wsm + Y.off_hard);
+
+    for (;;) {
+        unsigned long long fq = 0;
+        if (lane == 0) fq = atomicAdd(P.next, 1ull);
+        fq = pcl_shfl_u64(fq, 0);
+        if ((int64_t)fq >= P.F) break;
+        const int64_t f = (int64_t)fq;
+
+        const real* ch = P.llr + f * n;
+        for (int v = lane; v < n; v += 32) sllr[v] = ch[v];
+        __syncwarp();
+        for (int e = lane; e < E; e += 32) msg[e] = sllr[P.col[e]];   // decoder.py:144-146
+        __syncwarp();
+
+        int iters = Y.max_iter;                                       // :149
+        for (int it = 0; it < Y.max_iter; it++) {
+            // 1. check nodes (:152-168)
+            for (int c = lane; c < m; c += 32) {
+                const int e0 = P.cptr[c];
+                const int d = P.cptr[c + 1] - e0;
+                if (MODE == 1) {
+                    cn_ms<real>(msg + e0, d, P.norm);
+                } else {
+                    if (sizeof(real) == 8) cn_bp_exact<DMAX>((double*)(msg + e0), d);
+                    else cn_bp_f32<DMAX>((float*)(msg + e0), d);
+                }
+            }
+            __syncwarp();
+            // 2. variable nodes (:173-188) + 3. hard decision (:191)
+            for (int vb = 0; vb < n; vb += 32) {
+                const int v = vb + lane;
+                bool bit = false;
+                if (v < n) {
+                    const int j0 = P.vptr[v];
+                    const int d = P.vptr[v + 1] - j0;
+                    const uint16_t* ed = P.vperm + j0;
+                    real total;
+                    if (d == 3) {
+                        const int ea = ed[0], eb = ed[1], ec = ed[2];
+                        const real ma = msg[ea], mb = msg[eb], mc = msg[ec];
+                        total = sllr[v] + ((((real)0 + ma) + mb) + mc);
+                        msg[ea] = total - ma;
+                        msg[eb] = total - mb;
+                        msg[ec] = total - mc;
+                    } else {
+                        total = sllr[v] + vn_sum_np<real>(msg, ed, d);
+                        for (int j = 0; j < d; j++) {
+                            const int e = ed[j];
+                            msg[e] = total - msg[e];
+                        }
+                    }
+                    bit = (total <= (real)0);
+                    if (P.total != nullptr) P.total[f * n + v] = total;
+                }
+                const unsigned bal = __ballot_sync(PCL_FULL_MASK, bit);
+                if (lane == 0) hard[vb >> 5] = bal;
+            }
+            __syncwarp();
+            // 4. syndrome early stop (:194-198)
+            if (Y.early_stop) {
+                bool bad = false;
+                for (int c = lane; c < m; c += 32) {
+                    const int e0 = P.cptr[c], e1 = P.cptr[c + 1];
+                    unsigned par = 0;
+                    for (int e = e0; e < e1; e++) {
+                        const int v = P.col[e];
+                        par ^= hard[v >> 5] >> (v & 31);
+                    }
+                    bad |= (par & 1u) != 0;
+                }
+                if (!__any_sync(PCL_FULL_MASK, bad)) { iters = it + 1; break; }
+            }
+        }
+        uint8_t* out = P.bits + f * n;
+        for (int v = lane; v < n; v += 32) out[v] = (uint8_t)((hard[v >> 5] >> (v & 31)) & 1u);
+        if (P.iters != nullptr && lane == 0) P.iters[f] = iters;
+        __syncwarp();
+    }
+}

@@ -1,0 +1,677 @@
+// pcl_api.cu -- C ABI (include/pcl.h) over the sm_100a decoder kernels.
+//
+// Host side of the drop-in boundary: validates arguments the way the reference
+// constructors do, precomputes the code tables once per handle (decode-step-order
+// frozen mask and info gather map for polar; check-major / variable-major edge
+// tables for LDPC), sizes shared memory / scratch / grid for the B200 and launches
+// the kernels.  No torch types, no CPU decode path.
+#include "pcl_common.cuh"
+#include "polar_scl.cuh"
+#include "ldpc_bp.cuh"
+#include "../../include/pcl.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define PCL_VERSION_NUM 100
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t e_ = (expr);                                                        \
+        if (e_ != cudaSuccess)                                                          \
+            return fail(PCL_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+#ifdef PCL_EMU
+#define PCL_LAUNCH(kern, grid, block, smem, stream, arg) \
+    simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(arg); })
+static int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
+#else
+#define PCL_LAUNCH(kern, grid, block, smem, stream, arg) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(arg)
+static int env_int(const char* name, int dflt) { const char* s = getenv(name); return s ? atoi(s) : dflt; }
+#endif
+
+extern "C" int pcl_version(void) { return PCL_VERSION_NUM; }
+extern "C" const char* pcl_last_error(void) { return g_err.c_str(); }
+
+extern "C" int pcl_device_count(void)
+{
+#ifdef PCL_EMU
+    return 0;
+#else
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+#endif
+}
+
+struct DeviceInfo { int sms; int smem_per_sm; int smem_per_block; };
+
+static int device_info(DeviceInfo* di)
+{
+#ifdef PCL_EMU
+    di->sms = 2; di->smem_per_sm = 228 * 1024; di->smem_per_block = 227 * 1024;
+    return PCL_OK;
+#else
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di->sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di->smem_per_block, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return PCL_OK;
+#endif
+}
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+static inline int ilog2i(int v) { int n = 0; while ((1 << n) < v) n++; return n; }
+static inline int bit_reverse_i(int v, int nbits)
+{
+    int r = 0;
+    for (int i = 0; i < nbits; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+
+// =============================================================== polar =========
+#define PCL_NSTAGE 2
+
+struct pcl_polar {
+    int N, n, K, L, LP, dtype;
+    int crc_len; uint32_t crc_poly;
+    PolarLayout lay;
+    uint32_t* d_frozen_words = nullptr;
+    uint16_t* d_info_pos = nullptr;
+    void* d_scratch[PCL_NSTAGE] = {nullptr, nullptr};
+    size_t scratch_bytes = 0;
+    int wpb, grid_max, smem_bytes;
+    int last_grid = 0;
+    // host-buffer pipeline
+    void* d_llr[PCL_NSTAGE] = {nullptr, nullptr};
+    uint8_t* d_bits[PCL_NSTAGE] = {nullptr, nullptr};
+    int64_t chunk = 0;
+#ifndef PCL_EMU
+    cudaStream_t st[PCL_NSTAGE] = {nullptr, nullptr};
+#endif
+};
+
+static size_t real_size(int dtype) { return dtype == PCL_F64 ? 8 : 4; }
+
+static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int rsz, bool crc)
+{
+    Y.N = N; Y.n = ilog2i(N); Y.K = K; Y.L = L; Y.G = G;
+    Y.NW = N >= 32 ? N / 32 : 1;
+    Y.nb = Y.n > 5 ? Y.n - 5 : 0;
+    Y.uw_slots = crc ? LP : 1;
+    int off = 0;
+    Y.off_cm = off;     off += 2 * LP * 8;
+    Y.off_newpm = off;  off += LP * 8;
+    int llr_vals = (G >= Y.n - 1) ? 0 : LP * ((N >> G) - 2);
+    Y.off_llr = off;    off += align_up(llr_vals * rsz, 8);
+    Y.off_sel = off;    off += LP * 4;
+    Y.off_bw = off;     off += LP * (N >= 64 ? (N / 32 - 1) : 0) * 4;
+    Y.off_uw = off;     off += Y.uw_slots * Y.NW * 4;
+    Y.warp_bytes = align_up(off, 16);
+    Y.scratch_per_warp = (int64_t)LP * (N - (N >> G));
+}
+
+template <int LP, typename real>
+static int polar_launch_t(pcl_polar* h, const PolarParams<real>& P, int grid, void* stream)
+{
+    (void)stream;
+    auto kern = polar_scl_kernel<LP, real>;
+    PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+    return PCL_OK;
+}
+
+template <typename real>
+static int polar_launch(pcl_polar* h, const PolarParams<real>& P, int grid, void* stream)
+{
+    switch (h->LP) {
+        case 1: return polar_launch_t<1, real>(h, P, grid, stream);
+        case 2: return polar_launch_t<2, real>(h, P, grid, stream);
+        case 4: return polar_launch_t<4, real>(h, P, grid, stream);
+        case 8: return polar_launch_t<8, real>(h, P, grid, stream);
+        case 16: return polar_launch_t<16, real>(h, P, grid, stream);
+        case 32: return polar_launch_t<32, real>(h, P, grid, stream);
+    }
+    return fail(PCL_EUNSUPPORTED, "list size %d not supported (max 32)", h->L);
+}
+
+#ifndef PCL_EMU
+template <int LP, typename real>
+static int polar_occ_t(int threads, int smem, int* bps)
+{
+    CUDA_TRY(cudaFuncSetAttribute(polar_scl_kernel<LP, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, polar_scl_kernel<LP, real>, threads, smem));
+    return PCL_OK;
+}
+template <typename real>
+static int polar_occ(int LP, int threads, int smem, int* bps)
+{
+    switch (LP) {
+        case 1: return polar_occ_t<1, real>(threads, smem, bps);
+        case 2: return polar_occ_t<2, real>(threads, smem, bps);
+        case 4: return polar_occ_t<4, real>(threads, smem, bps);
+        case 8: return polar_occ_t<8, real>(threads, smem, bps);
+        case 16: return polar_occ_t<16, real>(threads, smem, bps);
+        case 32: return polar_occ_t<32, real>(threads, smem, bps);
+    }
+    return PCL_EUNSUPPORTED;
+}
+#endif
+
+extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
+                                int crc_len, uint32_t crc_poly, int dtype)
+{
+    if (!out || !frozen_mask) return fail(PCL_EINVAL, "null argument");
+    // src/polar/decoder.py:17-18, :194-196
+    if (N <= 0 || (N & (N - 1)) != 0) return fail(PCL_EINVAL, "N must be a power of 2");
+    if (!(K > 0 && K < N)) return fail(PCL_EINVAL, "K must be in (0, N)");
+    if (list_size < 1) return fail(PCL_EINVAL, "list_size must be >= 1");
+    if (list_size > 32) return fail(PCL_EUNSUPPORTED, "list_size %d > 32 is not supported by the one-warp-per-frame kernel", list_size);
+    if (N > 8192) return fail(PCL_EUNSUPPORTED, "N %d > 8192 is not supported", N);
+    if (dtype != PCL_F32 && dtype != PCL_F64) return fail(PCL_EINVAL, "bad dtype");
+    if (crc_len < 0 || crc_len > 32) return fail(PCL_EINVAL, "bad crc_len");
+    int n = ilog2i(N);
+    int nfree = 0;
+    for (int l = 0; l < N; l++) nfree += frozen_mask[l] == 0;
+    if (nfree != K) return fail(PCL_EINVAL, "frozen mask leaves %d info positions, K=%d", nfree, K);
+
+    pcl_polar* h = new pcl_polar();
+    h->N = N; h->n = n; h->K = K; h->L = list_size; h->dtype = dtype;
+    h->crc_len = crc_len; h->crc_poly = crc_poly;
+    int LP = 1;
+    while (LP < list_size) LP <<= 1;
+    h->LP = LP;
+
+    // decode-step-order tables: step i <-> reference index bit_reverse(i)
+    const int shift = N < 32 ? 32 - N : 0;
+    const int NW = N >= 32 ? N / 32 : 1;
+    std::vector<uint32_t> fw(NW, 0);
+    for (int i = 0; i < N; i++)
+        if (frozen_mask[bit_reverse_i(i, n)]) fw[(i + shift) >> 5] |= 1u << ((i + shift) & 31);
+    std::vector<uint16_t> ip;
+    for (int l = 0; l < N; l++)
+        if (!frozen_mask[l]) ip.push_back((uint16_t)bit_reverse_i(l, n));
+
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) { delete h; return rc; }
+    const int rsz = (int)real_size(dtype);
+    h->wpb = env_int("PCL_POLAR_WPB", 4);
+    if (h->wpb < 1 || h->wpb > 4) h->wpb = 4;
+    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", 9216);
+    int G = env_int("PCL_POLAR_G", -1);
+    if (G < 0) {
+        for (G = 0; G < n - 1; G++) {
+            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0);
+            if (h->lay.warp_bytes <= budget) break;
+        }
+    }
+    if (G > n - 1) G = n - 1;
+    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0);
+    h->smem_bytes = h->lay.warp_bytes * h->wpb;
+    if (h->smem_bytes > di.smem_per_block) {
+        delete h;
+        return fail(PCL_EUNSUPPORTED, "shared memory %d B per block exceeds the device limit", h->smem_bytes);
+    }
+    int bps = 1;
+#ifndef PCL_EMU
+    rc = (dtype == PCL_F64) ? polar_occ<double>(LP, h->wpb * 32, h->smem_bytes, &bps)
+                            : polar_occ<float>(LP, h->wpb * 32, h->smem_bytes, &bps);
+    if (rc) { delete h; return rc; }
+    if (bps < 1) { delete h; return fail(PCL_ECUDA, "kernel does not fit on an SM"); }
+#endif
+    h->grid_max = di.sms * bps;
+    h->scratch_bytes = (size_t)h->grid_max * h->wpb * h->lay.scratch_per_warp * rsz;
+
+    if (cudaMalloc((void**)&h->d_frozen_words, NW * 4) != cudaSuccess ||
+        cudaMalloc((void**)&h->d_info_pos, (size_t)K * 2) != cudaSuccess) {
+        pcl_polar_destroy(h);
+        return fail(PCL_ECUDA, "cudaMalloc failed (tables)");
+    }
+    if (cudaMemcpy(h->d_frozen_words, fw.data(), NW * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_info_pos, ip.data(), (size_t)K * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+        pcl_polar_destroy(h);
+        return fail(PCL_ECUDA, "cudaMemcpy failed (tables)");
+    }
+    if (h->scratch_bytes) {
+        if (cudaMalloc(&h->d_scratch[0], h->scratch_bytes) != cudaSuccess) {
+            pcl_polar_destroy(h);
+            return fail(PCL_ECUDA, "cudaMalloc failed (scratch %zu B)", h->scratch_bytes);
+        }
+    }
+    *out = h;
+    return PCL_OK;
+}
+
+extern "C" void pcl_polar_destroy(pcl_polar_t* h)
+{
+    if (!h) return;
+    cudaFree(h->d_frozen_words);
+    cudaFree(h->d_info_pos);
+    for (int s = 0; s < PCL_NSTAGE; s++) {
+        cudaFree(h->d_scratch[s]);
+        cudaFree(h->d_llr[s]);
+        cudaFree(h->d_bits[s]);
+#ifndef PCL_EMU
+        if (h->st[s]) cudaStreamDestroy(h->st[s]);
+#endif
+    }
+    delete h;
+}
+
+extern "C" int pcl_polar_lp(const pcl_polar_t* h) { return h ? h->LP : 0; }
+
+extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels)
+{
+    if (!h) return fail(PCL_EINVAL, "null handle");
+    if (grid) *grid = h->last_grid;
+    if (block) *block = h->wpb * 32;
+    if (smem_bytes) *smem_bytes = h->smem_bytes;
+    if (glevels) *glevels = h->lay.G;
+    return PCL_OK;
+}
+
+template <typename real>
+static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8_t* bits_dev, double* pm_dev,
+                             void* leaf_dev, uint8_t* parent_dev, void* scratch, void* stream)
+{
+    PolarParams<real> P;
+    P.lay = h->lay;
+    P.llr = (const real*)llr_dev;
+    P.bits = bits_dev;
+    P.pm_out = pm_dev;
+    P.dbg_leaf = (real*)leaf_dev;
+    P.dbg_parent = parent_dev;
+    P.frozen_words = h->d_frozen_words;
+    P.info_pos = h->d_info_pos;
+    P.scratch = (real*)scratch;
+    P.F = F;
+    P.want_pm = pm_dev != nullptr;
+    P.use_crc = h->crc_len > 0;
+    P.crc_len = h->crc_len;
+    P.crc_poly = h->crc_poly;
+    int64_t need = (F + h->wpb - 1) / h->wpb;
+    int grid = (int)std::min<int64_t>(need, h->grid_max);
+    h->last_grid = grid;
+    int rc = polar_launch<real>(h, P, grid, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return PCL_OK;
+}
+
+extern "C" int pcl_polar_decode_batch(pcl_polar_t* h, const void* llr_dev, int64_t F, uint8_t* bits_dev,
+                                      double* pm_dev, void* leaf_dev, uint8_t* parent_dev, void* stream)
+{
+    if (!h || F < 0) return fail(PCL_EINVAL, "bad handle or F");
+    if (F == 0) return PCL_OK;
+    if (!llr_dev || !bits_dev) return fail(PCL_EINVAL, "null buffer");
+    if ((leaf_dev == nullptr) != (parent_dev == nullptr)) return fail(PCL_EINVAL, "leaf_dev and parent_dev go together");
+    if (h->dtype == PCL_F64)
+        return polar_decode_impl<double>(h, llr_dev, F, bits_dev, pm_dev, leaf_dev, parent_dev, h->d_scratch[0], stream);
+    return polar_decode_impl<float>(h, llr_dev, F, bits_dev, pm_dev, leaf_dev, parent_dev, h->d_scratch[0], stream);
+}
+
+extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8_t* bits_host, void* stream)
+{
+    if (!h || F < 0) return fail(PCL_EINVAL, "bad handle or F");
+    if (F == 0) return PCL_OK;
+    if (!llr_host || !bits_host) return fail(PCL_EINVAL, "null buffer");
+#ifdef PCL_EMU
+    (void)stream;
+    return fail(PCL_ECUDA, "no CUDA device");
+#else
+    const size_t rsz = real_size(h->dtype);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 32768)));
+    if (h->chunk < chunk) {
+        for (int s = 0; s < PCL_NSTAGE; s++) {
+            cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]);
+            h->d_llr[s] = nullptr; h->d_bits[s] = nullptr;
+            CUDA_TRY(cudaMalloc(&h->d_llr[s], (size_t)chunk * h->N * rsz));
+            CUDA_TRY(cudaMalloc((void**)&h->d_bits[s], (size_t)chunk * h->K));
+        }
+        h->chunk = chunk;
+    }
+    for (int s = 0; s < PCL_NSTAGE; s++) {
+        if (!h->st[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->st[s], cudaStreamNonBlocking));
+        if (!h->d_scratch[s] && h->scratch_bytes) CUDA_TRY(cudaMalloc(&h->d_scratch[s], h->scratch_bytes));
+    }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int stage = 0;
+    for (int64_t f0 = 0; f0 < F; f0 += chunk, stage = (stage + 1) % PCL_NSTAGE) {
+        const int64_t fc = std::min<int64_t>(chunk, F - f0);
+        cudaStream_t st = h->st[stage];
+        CUDA_TRY(cudaMemcpyAsync(h->d_llr[stage], (const char*)llr_host + (size_t)f0 * h->N * rsz,
+                                 (size_t)fc * h->N * rsz, cudaMemcpyHostToDevice, st));
+        int rc = (h->dtype == PCL_F64)
+            ? polar_decode_impl<double>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st)
+            : polar_decode_impl<float>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(bits_host + (size_t)f0 * h->K, h->d_bits[stage], (size_t)fc * h->K,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < PCL_NSTAGE; s++) CUDA_TRY(cudaStreamSynchronize(h->st[s]));
+    return PCL_OK;
+#endif
+}
+
+// ================================================================ LDPC =========
+struct pcl_ldpc {
+    int m, n, E, mode, max_iter, early_stop, dtype, dmax;
+    double norm;
+    LdpcLayout lay;
+    int32_t* d_cptr = nullptr;
+    uint16_t* d_col = nullptr;
+    int32_t* d_vptr = nullptr;
+    uint16_t* d_vperm = nullptr;
+    unsigned long long* d_next[PCL_NSTAGE] = {nullptr, nullptr};
+    int wpb, grid_max, smem_bytes, last_grid = 0;
+    void* d_llr[PCL_NSTAGE] = {nullptr, nullptr};
+    uint8_t* d_bits[PCL_NSTAGE] = {nullptr, nullptr};
+    int32_t* d_iters[PCL_NSTAGE] = {nullptr, nullptr};
+    int64_t chunk = 0;
+#ifndef PCL_EMU
+    cudaStream_t st[PCL_NSTAGE] = {nullptr, nullptr};
+#endif
+};
+
+template <typename real, int MODE, int DMAX>
+static int ldpc_launch_t(pcl_ldpc* h, const LdpcParams<real>& P, int grid, void* stream)
+{
+    (void)stream;
+    auto kern = ldpc_decode_kernel<real, MODE, DMAX>;
+    PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+    return PCL_OK;
+}
+
+template <typename real>
+static int ldpc_launch(pcl_ldpc* h, const LdpcParams<real>& P, int grid, void* stream)
+{
+    if (h->mode == PCL_LDPC_MS) return ldpc_launch_t<real, 1, 8>(h, P, grid, stream);
+    if (h->dmax <= 8) return ldpc_launch_t<real, 0, 8>(h, P, grid, stream);
+    if (h->dmax <= 16) return ldpc_launch_t<real, 0, 16>(h, P, grid, stream);
+    return ldpc_launch_t<real, 0, 32>(h, P, grid, stream);
+}
+
+#ifndef PCL_EMU
+template <typename real, int MODE, int DMAX>
+static int ldpc_occ_t(int threads, int smem, int* bps)
+{
+    CUDA_TRY(cudaFuncSetAttribute(ldpc_decode_kernel<real, MODE, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, ldpc_decode_kernel<real, MODE, DMAX>, threads, smem));
+    return PCL_OK;
+}
+template <typename real>
+static int ldpc_occ(pcl_ldpc* h, int threads, int smem, int* bps)
+{
+    if (h->mode == PCL_LDPC_MS) return ldpc_occ_t<real, 1, 8>(threads, smem, bps);
+    if (h->dmax <= 8) return ldpc_occ_t<real, 0, 8>(threads, smem, bps);
+    if (h->dmax <= 16) return ldpc_occ_t<real, 0, 16>(threads, smem, bps);
+    return ldpc_occ_t<real, 0, 32>(threads, smem, bps);
+}
+#endif
+
+extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H, int mode, double normalization,
+                               int max_iter, int early_stop, int dtype)
+{
+    if (!out || !H) return fail(PCL_EINVAL, "null argument");
+    if (m <= 0 || n <= 0) return fail(PCL_EINVAL, "bad H shape");
+    if (mode != PCL_LDPC_BP && mode != PCL_LDPC_MS) return fail(PCL_EINVAL, "bad mode");
+    if (dtype != PCL_F32 && dtype != PCL_F64) return fail(PCL_EINVAL, "bad dtype");
+    if (max_iter < 1) return fail(PCL_EINVAL, "max_iter must be >= 1");
+    if (n > 65535) return fail(PCL_EUNSUPPORTED, "n > 65535 not supported");
+
+    // _build_tanner_graph (src/ldpc/decoder.py:35-60): row-major scan, H[i, j] == 1
+    std::vector<int32_t> cptr(m + 1, 0), vptr(n + 1, 0), vdeg(n, 0);
+    std::vector<uint16_t> col;
+    for (int c = 0; c < m; c++) {
+        for (int v = 0; v < n; v++)
+            if (H[(size_t)c * n + v] == 1) { col.push_back((uint16_t)v); vdeg[v]++; }
+        cptr[c + 1] = (int32_t)col.size();
+    }
+    const int E = (int)col.size();
+    if (E > 65535) return fail(PCL_EUNSUPPORTED, "more than 65535 edges not supported");
+    for (int v = 0; v < n; v++) vptr[v + 1] = vptr[v] + vdeg[v];
+    std::vector<uint16_t> vperm(E ? E : 1);
+    {
+        std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
+        for (int c = 0; c < m; c++)
+            for (int e = cptr[c]; e < cptr[c + 1]; e++) vperm[fill[col[e]]++] = (uint16_t)e;
+    }
+    int dmax = 0, vmax = 0;
+    for (int c = 0; c < m; c++) {
+        int d = cptr[c + 1] - cptr[c];
+        dmax = std::max(dmax, d);
+        if (mode == PCL_LDPC_MS && d == 1)
+            return fail(PCL_EDEGREE1, "zero-size array to reduction operation minimum which has no identity");
+    }
+    for (int v = 0; v < n; v++) vmax = std::max(vmax, vdeg[v]);
+    if (mode == PCL_LDPC_BP && dmax > 32) return fail(PCL_EUNSUPPORTED, "check degree %d > 32 not supported", dmax);
+    if (vmax > 128) return fail(PCL_EUNSUPPORTED, "variable degree %d > 128 not supported", vmax);
+
+    pcl_ldpc* h = new pcl_ldpc();
+    h->m = m; h->n = n; h->E = E; h->mode = mode; h->max_iter = max_iter; h->early_stop = early_stop ? 1 : 0;
+    h->dtype = dtype; h->dmax = dmax; h->norm = normalization;
+    const int rsz = (int)real_size(dtype);
+    LdpcLayout& Y = h->lay;
+    Y.m = m; Y.n = n; Y.E = E; Y.max_iter = max_iter; Y.early_stop = h->early_stop;
+    Y.nhw = (n + 31) / 32;
+    int off = 0;
+    Y.off_msg = off;  off += align_up(std::max(E, 1) * rsz, 8);
+    Y.off_llr = off;  off += align_up(n * rsz, 8);
+    Y.off_hard = off; off += Y.nhw * 4;
+    Y.warp_bytes = align_up(off, 16);
+
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) { delete h; return rc; }
+    h->wpb = env_int("PCL_LDPC_WPB", 4);
+    if (h->wpb < 1 || h->wpb > 8) h->wpb = 4;
+    while (h->wpb > 1 && Y.warp_bytes * h->wpb > di.smem_per_block) h->wpb >>= 1;
+    h->smem_bytes = Y.warp_bytes * h->wpb;
+    if (h->smem_bytes > di.smem_per_block) {
+        delete h;
+        return fail(PCL_EUNSUPPORTED, "code too large: %d B of shared memory per frame", Y.warp_bytes);
+    }
+    int bps = 1;
+#ifndef PCL_EMU
+    rc = (dtype == PCL_F64) ? ldpc_occ<double>(h, h->wpb * 32, h->smem_bytes, &bps)
+                            : ldpc_occ<float>(h, h->wpb * 32, h->smem_bytes, &bps);
+    if (rc) { delete h; return rc; }
+    if (bps < 1) { delete h; return fail(PCL_ECUDA, "kernel does not fit on an SM"); }
+#endif
+    h->grid_max = di.sms * bps;
+
+    bool ok = cudaMalloc((void**)&h->d_cptr, (m + 1) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&h->d_col, std::max(E, 1) * 2) == cudaSuccess &&
+              cudaMalloc((void**)&h->d_vptr, (n + 1) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&h->d_vperm, std::max(E, 1) * 2) == cudaSuccess &&
+              cudaMalloc((void**)&h->d_next[0], 8) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_cptr, cptr.data(), (m + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->d_vptr, vptr.data(), (n + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && E)
+        ok = cudaMemcpy(h->d_col, col.data(), (size_t)E * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(h->d_vperm, vperm.data(), (size_t)E * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { pcl_ldpc_destroy(h); return fail(PCL_ECUDA, "device table setup failed"); }
+    *out = h;
+    return PCL_OK;
+}
+
+extern "C" void pcl_ldpc_destroy(pcl_ldpc_t* h)
+{
+    if (!h) return;
+    cudaFree(h->d_cptr); cudaFree(h->d_col); cudaFree(h->d_vptr); cudaFree(h->d_vperm);
+    for (int s = 0; s < PCL_NSTAGE; s++) {
+        cudaFree(h->d_next[s]); cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
+#ifndef PCL_EMU
+        if (h->st[s]) cudaStreamDestroy(h->st[s]);
+#endif
+    }
+    delete h;
+}
+
+extern "C" int pcl_ldpc_num_edges(const pcl_ldpc_t* h) { return h ? h->E : 0; }
+
+extern "C" int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, int* smem_bytes)
+{
+    if (!h) return fail(PCL_EINVAL, "null handle");
+    if (grid) *grid = h->last_grid;
+    if (block) *block = h->wpb * 32;
+    if (smem_bytes) *smem_bytes = h->smem_bytes;
+    return PCL_OK;
+}
+
+template <typename real>
+static int ldpc_decode_impl(pcl_ldpc* h, const void* llr_dev, int64_t F, uint8_t* bits_dev, int32_t* iters_dev,
+                            void* total_dev, unsigned long long* next, void* stream)
+{
+    LdpcParams<real> P;
+    P.lay = h->lay;
+    P.llr = (const real*)llr_dev;
+    P.bits = bits_dev;
+    P.iters = iters_dev;
+    P.total = (real*)total_dev;
+    P.cptr = h->d_cptr; P.col = h->d_col; P.vptr = h->d_vptr; P.vperm = h->d_vperm;
+    P.next = next;
+    P.F = F;
+    P.norm = (real)h->norm;
+    CUDA_TRY(cudaMemsetAsync(next, 0, 8, (cudaStream_t)stream));
+    int64_t need = (F + h->wpb - 1) / h->wpb;
+    int grid = (int)std::min<int64_t>(need, h->grid_max);
+    h->last_grid = grid;
+    int rc = ldpc_launch<real>(h, P, grid, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return PCL_OK;
+}
+
+extern "C" int pcl_ldpc_decode_batch(pcl_ldpc_t* h, const void* llr_dev, int64_t F, uint8_t* bits_dev,
+                                     int32_t* iters_dev, void* total_dev, void* stream)
+{
+    if (!h || F < 0) return fail(PCL_EINVAL, "bad handle or F");
+    if (F == 0) return PCL_OK;
+    if (!llr_dev || !bits_dev) return fail(PCL_EINVAL, "null buffer");
+    if (h->dtype == PCL_F64)
+        return ldpc_decode_impl<double>(h, llr_dev, F, bits_dev, iters_dev, total_dev, h->d_next[0], stream);
+    return ldpc_decode_impl<float>(h, llr_dev, F, bits_dev, iters_dev, total_dev, h->d_next[0], stream);
+}
+
+extern "C" int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
+                                    int32_t* iters_host, void* stream)
+{
+    if (!h || F < 0) return fail(PCL_EINVAL, "bad handle or F");
+    if (F == 0) return PCL_OK;
+    if (!llr_host || !bits_host) return fail(PCL_EINVAL, "null buffer");
+#ifdef PCL_EMU
+    (void)stream; (void)iters_host;
+    return fail(PCL_ECUDA, "no CUDA device");
+#else
+    const size_t rsz = real_size(h->dtype);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 32768)));
+    if (h->chunk < chunk) {
+        for (int s = 0; s < PCL_NSTAGE; s++) {
+            cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
+            h->d_llr[s] = nullptr; h->d_bits[s] = nullptr; h->d_iters[s] = nullptr;
+            CUDA_TRY(cudaMalloc(&h->d_llr[s], (size_t)chunk * h->n * rsz));
+            CUDA_TRY(cudaMalloc((void**)&h->d_bits[s], (size_t)chunk * h->n));
+            CUDA_TRY(cudaMalloc((void**)&h->d_iters[s], (size_t)chunk * 4));
+        }
+        h->chunk = chunk;
+    }
+    for (int s = 0; s < PCL_NSTAGE; s++) {
+        if (!h->st[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->st[s], cudaStreamNonBlocking));
+        if (!h->d_next[s]) CUDA_TRY(cudaMalloc((void**)&h->d_next[s], 8));
+    }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int stage = 0;
+    for (int64_t f0 = 0; f0 < F; f0 += chunk, stage = (stage + 1) % PCL_NSTAGE) {
+        const int64_t fc = std::min<int64_t>(chunk, F - f0);
+        cudaStream_t st = h->st[stage];
+        CUDA_TRY(cudaMemcpyAsync(h->d_llr[stage], (const char*)llr_host + (size_t)f0 * h->n * rsz,
+                                 (size_t)fc * h->n * rsz, cudaMemcpyHostToDevice, st));
+        int rc = (h->dtype == PCL_F64)
+            ? ldpc_decode_impl<double>(h, h->d_llr[stage], fc, h->d_bits[stage], h->d_iters[stage], nullptr, h->d_next[stage], st)
+            : ldpc_decode_impl<float>(h, h->d_llr[stage], fc, h->d_bits[stage], h->d_iters[stage], nullptr, h->d_next[stage], st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(bits_host + (size_t)f0 * h->n, h->d_bits[stage], (size_t)fc * h->n,
+                                 cudaMemcpyDeviceToHost, st));
+        if (iters_host)
+            CUDA_TRY(cudaMemcpyAsync(iters_host + f0, h->d_iters[stage], (size_t)fc * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < PCL_NSTAGE; s++) CUDA_TRY(cudaStreamSynchronize(h->st[s]));
+    return PCL_OK;
+#endif
+}
+
+// ============================================================ error counters ===
+__global__ void __launch_bounds__(256) count_errors_kernel(const uint8_t* bits, const uint8_t* ref, int64_t F,
+                                                           int width, int ncmp, unsigned long long* counters)
+{
+    // one warp per frame row; warp-aggregated, then one atomic per warp per counter
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long be = 0, fe = 0, fr = 0;
+    for (int64_t f = wid; f < F; f += nw) {
+        const uint8_t* a = bits + f * width;
+        const uint8_t* b = ref + f * width;
+        unsigned e = 0;
+        for (int k = lane; k < ncmp; k += 32) e += (a[k] != b[k]);
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(PCL_FULL_MASK, e, o);
+        be += e;
+        fe += (e != 0);
+        fr += 1;
+    }
+    if (lane == 0 && fr) {
+        atomicAdd(&counters[0], be);
+        atomicAdd(&counters[1], fe);
+        atomicAdd(&counters[2], fr);
+        atomicAdd(&counters[3], fr * (unsigned long long)ncmp);
+    }
+}
+
+struct CountArgs { const uint8_t* bits; const uint8_t* ref; int64_t F; int width; int ncmp; unsigned long long* c; };
+#ifdef PCL_EMU
+static void count_errors_emu(CountArgs a) { count_errors_kernel(a.bits, a.ref, a.F, a.width, a.ncmp, a.c); }
+#endif
+
+extern "C" int pcl_count_errors(const uint8_t* bits_dev, const uint8_t* ref_dev, int64_t F, int width, int ncmp,
+                                unsigned long long* counters_dev, void* stream)
+{
+    if (F < 0 || width <= 0 || ncmp < 0 || ncmp > width) return fail(PCL_EINVAL, "bad shape");
+    if (F == 0) return PCL_OK;
+    if (!bits_dev || !ref_dev || !counters_dev) return fail(PCL_EINVAL, "null buffer");
+    int grid = (int)std::min<int64_t>((F + 7) / 8, 148 * 8);
+#ifdef PCL_EMU
+    (void)stream;
+    CountArgs a{bits_dev, ref_dev, F, width, ncmp, counters_dev};
+    PCL_LAUNCH(count_errors_emu, grid, 256, 0, stream, a);
+#else
+    count_errors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits_dev, ref_dev, F, width, ncmp, counters_dev);
+    CUDA_TRY(cudaGetLastError());
+#endif
+    return PCL_OK;
+}
+
+#ifdef PCL_EMU
+extern "C" void simt_set_reverse(int r) { simt::reverse_order() = r != 0; }
+#endif

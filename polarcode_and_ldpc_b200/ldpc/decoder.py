@@ -1,0 +1,172 @@
+"""Drop-in BPDecoder / MSDecoder backed by the sm_100a kernel.
+
+Mirrors /root/reference/src/ldpc/decoder.py: BPDecoder(H, max_iter=50,
+early_stop=True) (:18) with decode(llr, return_iterations=False) (:124) and
+MSDecoder(H, max_iter=50, normalization=1.0, early_stop=True) (:215-216) with
+decode(llr) (:289).  Both return the whole n-bit codeword as np.int64 (:191,
+:200-202, :344, :352).  decode_batch(llr[F, n]) is the batched entry point; row f
+equals decode(llr[f]).
+
+Error behaviour kept from the reference: AssertionError on a wrong LLR length
+(:135, :299); ValueError when Min-Sum meets a degree-1 check (np.min of an empty
+array, :282); UnboundLocalError for max_iter < 1 (:200 reads an unbound name).
+Limits (NotImplementedError): n and edge count < 65536, BP check degree <= 32,
+variable degree <= 128.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from .. import _native
+
+
+class _LdpcBase:
+    _MODE = _native.PCL_LDPC_BP
+
+    def _setup(self, H, max_iter, normalization, early_stop, dtype, device):
+        self.H = H
+        self.m, self.n = H.shape
+        self.max_iter = max_iter
+        self.early_stop = early_stop
+        self._build_tanner_graph()
+        self._torch = _native.require_cuda()
+        torch = self._torch
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.dtype_name = str(dtype or _native.default_dtype()).replace("torch.", "")
+        self._code = _native.dtype_code(self.dtype_name)
+        self._tdtype = torch.float64 if self._code == _native.PCL_F64 else torch.float32
+        self._h = ctypes.c_void_p()
+        self._deferred = None
+        H8 = np.ascontiguousarray(np.asarray(H) == 1, dtype=np.uint8)
+        if max_iter < 1:
+            # the reference constructs fine and fails inside decode()
+            self._deferred = UnboundLocalError("cannot access local variable 'decoded' where it is not "
+                                               "associated with a value")
+            return
+        with torch.cuda.device(self.device):
+            rc = _native.lib().pcl_ldpc_create(ctypes.byref(self._h), self.m, self.n,
+                                               ctypes.c_void_p(H8.ctypes.data), self._MODE,
+                                               ctypes.c_double(float(normalization)), int(max_iter),
+                                               int(bool(early_stop)), self._code)
+        if rc == _native.PCL_EDEGREE1:
+            # raised by the reference at decode time, not at construction
+            self._deferred = ValueError("zero-size array to reduction operation minimum which has no identity")
+            return
+        _native.check(rc)
+
+    def _build_tanner_graph(self):
+        """Adjacency lists in the reference's order (decoder.py:35-60)."""
+        Hb = np.asarray(self.H) == 1
+        self.check_neighbors = [list(np.flatnonzero(Hb[c])) for c in range(self.m)]
+        self.var_neighbors = [list(np.flatnonzero(Hb[:, v])) for v in range(self.n)]
+        self.var_to_check_idx = [{c: i for i, c in enumerate(nb)} for nb in self.var_neighbors]
+        self.check_to_var_idx = [{v: i for i, v in enumerate(nb)} for nb in self.check_neighbors]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _native.lib().pcl_ldpc_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _to_device(self, llr):
+        torch = self._torch
+        if isinstance(llr, torch.Tensor):
+            t = llr
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(llr, dtype=np.float64)))
+        assert t.dim() == 2 and t.shape[1] == self.n, f"LLR length must be {self.n}"
+        return t.to(device=self.device, non_blocking=True).to(self._tdtype).contiguous()
+
+    def _run(self, llr_dev, want_total: bool):
+        if self._deferred is not None:
+            raise self._deferred
+        torch = self._torch
+        F = llr_dev.shape[0]
+        bits = torch.empty((F, self.n), dtype=torch.uint8, device=self.device)
+        iters = torch.empty((F,), dtype=torch.int32, device=self.device)
+        total = torch.empty((F, self.n), dtype=self._tdtype, device=self.device) if want_total else None
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.check(_native.lib().pcl_ldpc_decode_batch(
+                self._h, ptr(llr_dev), F, ptr(bits), ptr(iters), ptr(total), ctypes.c_void_p(stream)))
+        return bits, iters, total
+
+    def decode_batch(self, llr, return_iterations: bool = False, return_total_llr: bool = False):
+        """llr[F, n] -> bits[F, n] (+ iterations[F], + total LLRs of the last iteration)."""
+        on_device = isinstance(llr, self._torch.Tensor) and llr.is_cuda
+        bits, iters, total = self._run(self._to_device(llr), return_total_llr)
+        out = [bits if on_device else bits.cpu().numpy().astype(np.int64)]
+        if return_iterations:
+            out.append(iters if on_device else iters.cpu().numpy().astype(np.int64))
+        if return_total_llr:
+            out.append(total if on_device else total.double().cpu().numpy())
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def decode_batch_host(self, llr_host, bits_host=None, iters_host=None):
+        """C-ABI host-buffer path (chunked, overlapped H2D / decode / D2H)."""
+        if self._deferred is not None:
+            raise self._deferred
+        torch = self._torch
+        if not isinstance(llr_host, torch.Tensor):
+            llr_host = torch.from_numpy(np.ascontiguousarray(llr_host))
+        assert llr_host.dim() == 2 and llr_host.shape[1] == self.n and llr_host.dtype == self._tdtype
+        assert llr_host.device.type == "cpu" and llr_host.is_contiguous()
+        F = llr_host.shape[0]
+        if bits_host is None:
+            bits_host = torch.empty((F, self.n), dtype=torch.uint8, pin_memory=True)
+        ip = ctypes.c_void_p(iters_host.data_ptr()) if iters_host is not None else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.check(_native.lib().pcl_ldpc_decode_host(
+                self._h, ctypes.c_void_p(llr_host.data_ptr()), F, ctypes.c_void_p(bits_host.data_ptr()), ip,
+                ctypes.c_void_p(stream)))
+        return bits_host
+
+    def launch_info(self) -> dict:
+        g, b, s = (ctypes.c_int() for _ in range(3))
+        _native.check(_native.lib().pcl_ldpc_launch_info(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value,
+                "edges": _native.lib().pcl_ldpc_num_edges(self._h)}
+
+
+class BPDecoder(_LdpcBase):
+    """Flooding sum-product decoder (reference: src/ldpc/decoder.py:11-205)."""
+    _MODE = _native.PCL_LDPC_BP
+
+    def __init__(self, H: np.ndarray, max_iter: int = 50, early_stop: bool = True, dtype=None, device=None):
+        self._setup(H, max_iter, 1.0, early_stop, dtype, device)
+
+    def decode(self, llr: np.ndarray, return_iterations: bool = False):
+        assert len(llr) == self.n, f"LLR length must be {self.n}"
+        bits, iters, _ = self._run(self._to_device(np.asarray(llr, dtype=np.float64)[None, :]), False)
+        decoded = bits[0].cpu().numpy().astype(np.int64)
+        if return_iterations:
+            return decoded, int(iters[0].item())
+        return decoded
+
+    def __repr__(self) -> str:
+        return f"BPDecoder(n={self.n}, m={self.m}, max_iter={self.max_iter})"
+
+
+class MSDecoder(_LdpcBase):
+    """Normalised Min-Sum decoder (reference: src/ldpc/decoder.py:208-355)."""
+    _MODE = _native.PCL_LDPC_MS
+
+    def __init__(self, H: np.ndarray, max_iter: int = 50, normalization: float = 1.0,
+                 early_stop: bool = True, dtype=None, device=None):
+        self.normalization = normalization
+        self._setup(H, max_iter, normalization, early_stop, dtype, device)
+
+    def decode(self, llr: np.ndarray) -> np.ndarray:
+        assert len(llr) == self.n, f"LLR length must be {self.n}"
+        bits, _, _ = self._run(self._to_device(np.asarray(llr, dtype=np.float64)[None, :]), False)
+        return bits[0].cpu().numpy().astype(np.int64)
+
+    def __repr__(self) -> str:
+        return f"MSDecoder(n={self.n}, m={self.m}, max_iter={self.max_iter}, norm={self.normalization})"
