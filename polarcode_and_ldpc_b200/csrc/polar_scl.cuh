@@ -4,7 +4,7 @@
 // SCLDecoder.decode (:225-262, with _decode_frozen_bit :264-281,
 // _decode_info_bit :283-339, _log_likelihood :374-406) for a whole batch.
 //
-// Formulation (validated against the reference through oracle/pcl_oracle.c):
+// Formulation (validated against the reference's own outputs, see tests/):
 // decode step i <-> reference bit index l = bit_reverse(i); level d = stage s+1;
 // in decode-step order every node's halves are contiguous, so the reference's
 // stage-s butterfly at distance 2^s becomes dst[k] = f/g(src[k], src[k+sz]) with
