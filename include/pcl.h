@@ -71,8 +71,11 @@ int pcl_polar_decode_batch(pcl_polar_t* h, const void* llr_dev, int64_t F, uint8
 int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
                           void* stream);
 int pcl_polar_lp(const pcl_polar_t* h);
-/* Launch geometry of the last decode (for gpu_launches / occupancy reporting). */
-int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels);
+/* Launch geometry of the last decode (for gpu_launches / occupancy reporting): grid, block,
+ * dynamic shared memory, number of tree levels kept in the L2 scratch, and whether the
+ * register-resident-bottom kernel (1) or the generic kernel (0) is in use. */
+int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
+                          int* fast);
 
 /*
  * BPDecoder.__init__ / MSDecoder.__init__ + _build_tanner_graph

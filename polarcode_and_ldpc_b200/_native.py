@@ -44,7 +44,7 @@ def lib() -> ctypes.CDLL:
     L.pcl_polar_decode_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     L.pcl_polar_decode_host.argtypes = [vp, vp, i64, vp, vp]
     L.pcl_polar_lp.argtypes = [vp]
-    L.pcl_polar_launch_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 4
+    L.pcl_polar_launch_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 5
     L.pcl_ldpc_create.argtypes = [ctypes.POINTER(vp), i32, i32, vp, i32, ctypes.c_double, i32, i32, i32]
     L.pcl_ldpc_destroy.argtypes = [vp]
     L.pcl_ldpc_destroy.restype = None

@@ -92,6 +92,45 @@ PCL_DEVICE void cn_bp_exact(double* msg, int d)
 }
 
 // ---- check node, fp32 production rule (t and w = 1 - |t| side by side) ---------
+// MUFU budget per edge: ex2 + rcp on the way in, rcp + lg2 on the way out.
+//   u = exp(-|x|) (split-constant range reduction, rel. err ~1e-7)
+//   w = 1 - tanh(|x|/2) = 2u / (1 + u)   keeps full RELATIVE precision near |t| -> 1,
+//   t = (1 - u) / (1 + u)                keeps full ABSOLUTE precision near t -> 0.
+// Leave-one-out: p_i = prod t_j, q_i = 1 - prod (1 - w_j) (sums of positive terms, no
+// cancellation).  Output 2 atanh(p): q < 1/4 -> ln((2-q)/q); |p| < 1/4 -> odd series;
+// otherwise ln((1+|p|)/(1-|p|)).  Both clips of the reference (+-0.999999 on t and on the
+// product, decoder.py:82,88) become w >= 1e-6 and q >= 1e-6.
+PCL_DEVICE float pcl_ex2(float x)
+{
+#ifdef PCL_EMU
+    return exp2f(x);
+#else
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+PCL_DEVICE float pcl_lg2(float x)
+{
+#ifdef PCL_EMU
+    return log2f(x);
+#else
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+PCL_DEVICE float pcl_rcp(float x)
+{
+#ifdef PCL_EMU
+    return 1.0f / x;
+#else
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+
 template <int DMAX>
 PCL_DEVICE void cn_bp_f32(float* msg, int d)
 {
@@ -100,12 +139,17 @@ PCL_DEVICE void cn_bp_f32(float* msg, int d)
     for (int j = 0; j < DMAX; j++) {
         if (j < d) {
             const float x = msg[j];
-            float tv = tanhf(0.5f * x);
-            tv = fminf(fmaxf(tv, -0.999999f), 0.999999f);
-            const float u = expf(-fabsf(x));
-            float wv = (2.0f * u) / (1.0f + u);                // 1 - tanh(|x|/2)
-            t[j] = tv;
-            w[j] = fmaxf(wv, 1e-6f);
+            const float a = fabsf(x);
+            // -a * log2(e) as hi + lo
+            const float th = a * -1.4426950216293335f;
+            const float tl = fmaf(a, -1.4426950216293335f, -th) + a * -1.9259629911266175e-8f;
+            float u = pcl_ex2(th);
+            u = fmaf(u, tl * 0.6931471805599453f, u);
+            const float r = pcl_rcp(1.0f + u);
+            const float wv = fmaxf(2.0f * u * r, 1e-6f);       // 1 - |t|, clipped
+            float tv = fminf((1.0f - u) * r, 0.999999f);       // |t|, clipped
+            t[j] = (x < 0.0f) ? -tv : tv;
+            w[j] = wv;
         } else {
             t[j] = 1.0f;
             w[j] = 0.0f;
@@ -125,16 +169,18 @@ PCL_DEVICE void cn_bp_f32(float* msg, int d)
     for (int i = 0; i < DMAX; i++) {
         if (i < d) {
             const float pr = pt * st[i + 1];
+            const float ap = fabsf(pr);
             float q = fmaf(-pq, sq[i + 1], pq + sq[i + 1]);
-            float o;
-            if (q < 0.25f) {
-                q = fmaxf(q, 1e-6f);                            // |p| <= 0.999999
-                const float mag = logf((2.0f - q) / q);         // 2 atanh(1 - q)
-                o = (pr < 0.0f) ? -mag : mag;
-            } else {
-                o = 2.0f * atanhf(pr);
-            }
-            msg[i] = o;
+            q = fmaxf(q, 1e-6f);                                // |p| <= 0.999999
+            const bool near1 = q < 0.25f;
+            const float num = near1 ? 2.0f - q : 1.0f + ap;
+            const float den = near1 ? q : 1.0f - ap;
+            float mag = 0.6931471805599453f * pcl_lg2(num * pcl_rcp(den));
+            const float p2 = ap * ap;
+            const float ser = 2.0f * ap * fmaf(p2, fmaf(p2, fmaf(p2, fmaf(p2, 0.11111111f, 0.14285715f), 0.2f),
+                                                        0.33333334f), 1.0f);
+            if (!near1 && ap < 0.25f) mag = ser;
+            msg[i] = (pr < 0.0f) ? -mag : mag;
         }
         pt = pt * t[i];
         pq = fmaf(-pq, w[i], pq + w[i]);

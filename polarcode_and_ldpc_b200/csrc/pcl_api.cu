@@ -7,6 +7,7 @@
 // the kernels.  No torch types, no CPU decode path.
 #include "pcl_common.cuh"
 #include "polar_scl.cuh"
+#include "polar_scl_fast.cuh"
 #include "ldpc_bp.cuh"
 #include "../../include/pcl.h"
 
@@ -103,6 +104,7 @@ struct pcl_polar {
     size_t scratch_bytes = 0;
     int wpb, grid_max, smem_bytes;
     int last_grid = 0;
+    int fast = 0;               // register-resident tree bottom (polar_scl_fast.cuh)
     // host-buffer pipeline
     void* d_llr[PCL_NSTAGE] = {nullptr, nullptr};
     uint8_t* d_bits[PCL_NSTAGE] = {nullptr, nullptr};
@@ -114,7 +116,7 @@ struct pcl_polar {
 
 static size_t real_size(int dtype) { return dtype == PCL_F64 ? 8 : 4; }
 
-static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int rsz, bool crc)
+static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int rsz, bool crc, bool fast = false)
 {
     Y.N = N; Y.n = ilog2i(N); Y.K = K; Y.L = L; Y.G = G;
     Y.NW = N >= 32 ? N / 32 : 1;
@@ -123,7 +125,9 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
     int off = 0;
     Y.off_cm = off;     off += 2 * LP * 8;
     Y.off_newpm = off;  off += LP * 8;
-    int llr_vals = (G >= Y.n - 1) ? 0 : LP * ((N >> G) - 2);
+    // generic kernel keeps levels G+1 .. n-1 in shared memory, the fast one G+1 .. n-4
+    int llr_vals = fast ? ((G >= Y.n - 4) ? 0 : LP * ((N >> G) - 16))
+                        : ((G >= Y.n - 1) ? 0 : LP * ((N >> G) - 2));
     Y.off_llr = off;    off += align_up(llr_vals * rsz, 8);
     Y.off_sel = off;    off += LP * 4;
     Y.off_bw = off;     off += LP * (N >= 64 ? (N / 32 - 1) : 0) * 4;
@@ -136,8 +140,13 @@ template <int LP, typename real>
 static int polar_launch_t(pcl_polar* h, const PolarParams<real>& P, int grid, void* stream)
 {
     (void)stream;
-    auto kern = polar_scl_kernel<LP, real>;
-    PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+    if (h->fast) {
+        auto kern = polar_scl_fast_kernel<LP, real>;
+        PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+    } else {
+        auto kern = polar_scl_kernel<LP, real>;
+        PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+    }
     return PCL_OK;
 }
 
@@ -157,22 +166,27 @@ static int polar_launch(pcl_polar* h, const PolarParams<real>& P, int grid, void
 
 #ifndef PCL_EMU
 template <int LP, typename real>
-static int polar_occ_t(int threads, int smem, int* bps)
+static int polar_occ_t(int fast, int threads, int smem, int* bps)
 {
-    CUDA_TRY(cudaFuncSetAttribute(polar_scl_kernel<LP, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, polar_scl_kernel<LP, real>, threads, smem));
+    if (fast) {
+        CUDA_TRY(cudaFuncSetAttribute(polar_scl_fast_kernel<LP, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, polar_scl_fast_kernel<LP, real>, threads, smem));
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(polar_scl_kernel<LP, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, polar_scl_kernel<LP, real>, threads, smem));
+    }
     return PCL_OK;
 }
 template <typename real>
-static int polar_occ(int LP, int threads, int smem, int* bps)
+static int polar_occ(int LP, int fast, int threads, int smem, int* bps)
 {
     switch (LP) {
-        case 1: return polar_occ_t<1, real>(threads, smem, bps);
-        case 2: return polar_occ_t<2, real>(threads, smem, bps);
-        case 4: return polar_occ_t<4, real>(threads, smem, bps);
-        case 8: return polar_occ_t<8, real>(threads, smem, bps);
-        case 16: return polar_occ_t<16, real>(threads, smem, bps);
-        case 32: return polar_occ_t<32, real>(threads, smem, bps);
+        case 1: return polar_occ_t<1, real>(fast, threads, smem, bps);
+        case 2: return polar_occ_t<2, real>(fast, threads, smem, bps);
+        case 4: return polar_occ_t<4, real>(fast, threads, smem, bps);
+        case 8: return polar_occ_t<8, real>(fast, threads, smem, bps);
+        case 16: return polar_occ_t<16, real>(fast, threads, smem, bps);
+        case 32: return polar_occ_t<32, real>(fast, threads, smem, bps);
     }
     return PCL_EUNSUPPORTED;
 }
@@ -218,16 +232,24 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     const int rsz = (int)real_size(dtype);
     h->wpb = env_int("PCL_POLAR_WPB", 4);
     if (h->wpb < 1 || h->wpb > 4) h->wpb = 4;
+    // Fast kernel: tree bottom in registers; needs N >= 16 and the packed 32-bit slot
+    // pointers to hold (n-4) LLR-level fields and (n-5) left-level fields of log2(LP) bits.
+    int pb = 0;
+    while ((1 << pb) < LP) pb++;
+    h->fast = (n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 &&
+               env_int("PCL_POLAR_GENERIC", 0) == 0) ? 1 : 0;
+    const int gmax = h->fast ? n - 4 : n - 1;
     int budget = env_int("PCL_POLAR_SMEM_PER_WARP", 9216);
     int G = env_int("PCL_POLAR_G", -1);
     if (G < 0) {
-        for (G = 0; G < n - 1; G++) {
-            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0);
+        for (G = 0; G < gmax; G++) {
+            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast);
             if (h->lay.warp_bytes <= budget) break;
         }
     }
-    if (G > n - 1) G = n - 1;
-    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0);
+    if (G > gmax) G = gmax;
+    if (G < 0) G = 0;
+    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast);
     h->smem_bytes = h->lay.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
         delete h;
@@ -235,8 +257,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     }
     int bps = 1;
 #ifndef PCL_EMU
-    rc = (dtype == PCL_F64) ? polar_occ<double>(LP, h->wpb * 32, h->smem_bytes, &bps)
-                            : polar_occ<float>(LP, h->wpb * 32, h->smem_bytes, &bps);
+    rc = (dtype == PCL_F64) ? polar_occ<double>(LP, h->fast, h->wpb * 32, h->smem_bytes, &bps)
+                            : polar_occ<float>(LP, h->fast, h->wpb * 32, h->smem_bytes, &bps);
     if (rc) { delete h; return rc; }
     if (bps < 1) { delete h; return fail(PCL_ECUDA, "kernel does not fit on an SM"); }
 #endif
@@ -281,9 +303,11 @@ extern "C" void pcl_polar_destroy(pcl_polar_t* h)
 
 extern "C" int pcl_polar_lp(const pcl_polar_t* h) { return h ? h->LP : 0; }
 
-extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels)
+extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
+                                     int* fast)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
+    if (fast) *fast = h->fast;
     if (grid) *grid = h->last_grid;
     if (block) *block = h->wpb * 32;
     if (smem_bytes) *smem_bytes = h->smem_bytes;

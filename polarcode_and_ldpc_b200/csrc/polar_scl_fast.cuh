@@ -1,0 +1,475 @@
+// polar_scl_fast.cuh -- SC / SCL decoder, one warp per frame, register-resident tree bottom.
+//
+// Same algorithm, list semantics and memory layout as polar_scl.cuh (read that header
+// first); what changes is where the work of the lowest three tree levels happens.  The
+// generic kernel was issue-bound (ncu: 515 k warp instructions per N=1024 L=8 frame, 3.0
+// IPC): 7 of every 8 level visits touch a node of <= 4 LLRs per path and paid loop,
+// address and packed-pointer arithmetic plus a shared-memory round trip each.  Here the
+// tree is cut at height 3: the decoder walks N/8 blocks of 8 leaves.
+//   * levels above the cut (node size >= 16) -- unchanged: [k][slot] arrays in shared
+//     memory / L2 scratch, lazily shared between paths through packed slot pointers;
+//   * the block root (8 LLRs per path) is produced straight into registers, and the
+//     levels of size 4, 2, 1 below it live in registers of the S = 32/LP lanes that own
+//     the path.  Butterflies whose two operands sit in the same lane are plain register
+//     ops; the others take one shuffle.  The 8 leaves are fully unrolled, so every stage,
+//     partial-sum bit position and live-register set is a compile-time constant;
+//   * a surviving path inherits its parent's live registers with shuffles (2 on average)
+//     together with ONE packed 64-bit pointer word (LLR levels low half, partial-sum
+//     levels high half) and the 32-bit small partial-sum word.
+// Path metric in fp64; fp32 build evaluates log1p(exp(-|x|)) as 2 atanh(u / (2 + u)) with
+// u = 2^(-|x| log2 e) (one ex2, one rcp, 6 FMA; |error| < 1e-7).
+#pragma once
+#include "pcl_common.cuh"
+#include "polar_scl.cuh"
+
+// ---- fast softplus(-|x|) ------------------------------------------------------------
+PCL_DEVICE float pcl_ex2f(float x)
+{
+#ifdef PCL_EMU
+    return exp2f(x);
+#else
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+PCL_DEVICE float pcl_rcpf(float x)
+{
+#ifdef PCL_EMU
+    return 1.0f / x;
+#else
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+
+template <typename real> struct pcl_fast;
+template <> struct pcl_fast<float> {
+    static PCL_DEVICE float softplus_neg_abs(float ax)
+    {
+        const float u = pcl_ex2f(ax * -1.4426950408889634f);      // exp(-|x|) in (0, 1]
+        const float s = u * pcl_rcpf(2.0f + u);                   // log1p(u) = 2 atanh(s), s <= 1/3
+        const float s2 = s * s;
+        float pl = fmaf(s2, 0.07692308f, 0.09090909f);
+        pl = fmaf(s2, pl, 0.11111111f);
+        pl = fmaf(s2, pl, 0.14285715f);
+        pl = fmaf(s2, pl, 0.2f);
+        pl = fmaf(s2, pl, 0.33333334f);
+        pl = fmaf(s2, pl, 1.0f);
+        return 2.0f * s * pl;
+    }
+    // b + (bit ? -a : a) with the sign flip done on the bit pattern
+    static PCL_DEVICE float g(float a, float b, uint32_t bit)
+    {
+        return b + __uint_as_float(__float_as_uint(a) ^ (bit << 31));
+    }
+};
+template <> struct pcl_fast<double> {
+    static PCL_DEVICE double softplus_neg_abs(double ax) { return log1p(exp(-ax)); }
+    static PCL_DEVICE double g(double a, double b, uint32_t bit) { return bit ? b - a : b + a; }
+};
+
+template <typename real>
+PCL_DEVICE real pcl_shfl_real(real v, int src);
+template <>
+PCL_DEVICE float pcl_shfl_real<float>(float v, int src) { return __shfl_sync(PCL_FULL_MASK, v, src); }
+template <>
+PCL_DEVICE double pcl_shfl_real<double>(double v, int src)
+{
+    return __longlong_as_double((long long)pcl_shfl_u64((uint64_t)__double_as_longlong(v), src));
+}
+
+// One butterfly stage inside the register-resident block: level of size Z from the level
+// of size 2Z.  S lanes own a path; element k of a level of size z lives in lane (k % S),
+// register (k / S) when z >= S, and in lane k, register 0 when z < S.
+template <int LP, int S, int Z, typename real>
+PCL_DEVICE void pcl_block_stage(real* dst, const real* src, bool is_g, uint32_t small, int kk, int lane)
+{
+    if (Z >= S) {
+        constexpr int CNT = (Z >= S) ? Z / S : 1;
+#pragma unroll
+        for (int t = 0; t < CNT; t++) {
+            const real a = src[t], b = src[t + CNT];
+            if (is_g) {
+                const uint32_t ub = (small >> (32 - 2 * Z + kk + S * t)) & 1u;
+                dst[t] = pcl_fast<real>::g(a, b, ub);
+            } else {
+                dst[t] = pcl_math<real>::f(a, b);
+            }
+        }
+    } else {
+        const real a = src[0];
+        const real b = pcl_shfl_real<real>(a, lane + Z * LP);     // element k + Z lives Z sub-lanes up
+        if (is_g) {
+            const uint32_t ub = (small >> ((32 - 2 * Z + kk) & 31)) & 1u;
+            dst[0] = pcl_fast<real>::g(a, b, ub);
+        } else {
+            dst[0] = pcl_math<real>::f(a, b);
+        }
+    }
+}
+
+template <int LP, typename real>
+__global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P)
+{
+    constexpr int PB = pcl_log2<LP>::v;
+    constexpr int S = 32 / LP;
+    constexpr int E3 = (8 >= S) ? 8 / S : 1;     // registers per lane for the size-8 level
+    constexpr int E2 = (4 >= S) ? 4 / S : 1;
+    constexpr int E1 = (2 >= S) ? 2 / S : 1;
+    const PolarLayout& Y = P.lay;
+    const int N = Y.N, n = Y.n, K = Y.K, L = Y.L, G = Y.G, NW = Y.NW, nb = Y.nb;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int p = lane & (LP - 1);
+    const int kk = lane >> PB;
+    const int shift = (N < 32) ? 32 - N : 0;
+    const int NB = N >> 3;
+
+    unsigned char* wsm = pcl_dyn_smem() + (size_t)warp * Y.warp_bytes;
+    double* cm = (double*)(wsm + Y.off_cm);
+    double* newpm = (double*)(wsm + Y.off_newpm);
+    int* sel = (int*)(wsm + Y.off_sel);
+    real* sl = (real*)(wsm + Y.off_llr);          // levels G+1 .. n-4
+    uint32_t* bw = (uint32_t*)(wsm + Y.off_bw);   // big left levels 1 .. nb
+    uint32_t* uw = (uint32_t*)(wsm + Y.off_uw);   // final u words
+    real* gl = P.scratch + (int64_t)(blockIdx.x * wpb + warp) * Y.scratch_per_warp;
+
+    const double NEG_INF = -(double)pcl_math<real>::inf();
+
+    for (int64_t f = (int64_t)blockIdx.x * wpb + warp; f < P.F; f += (int64_t)gridDim.x * wpb) {
+        const real* y = P.llr + f * N;
+        int nact = 1;
+        bool act = (p == 0);
+        double pm = act ? 0.0 : NEG_INF;
+        uint32_t ptrL = 0, ptrB = 0;              // packed slot pointers: LLR levels / left levels
+        uint32_t small = 0, ulast = 0;
+        uint32_t fw = 0;
+
+        for (int blk = 0; blk < NB; blk++) {
+            const int i0 = blk << 3;
+            if (((i0 + shift) & 31) == 0 || blk == 0) fw = P.frozen_words[(i0 + shift) >> 5];
+            const uint32_t fz8 = (fw >> ((i0 + shift) & 31)) & 0xffu;
+
+            // ---- levels above the cut: start .. n-3; the last one lands in registers ----
+            real R3[E3];
+#pragma unroll
+            for (int t = 0; t < E3; t++) R3[t] = (real)0;
+            const int start = (blk == 0) ? 1 : n - (__ffs(i0) - 1);
+            for (int d = start; d <= n - 3; d++) {
+                const int sz = N >> d;
+                const int bit = (i0 >> (n - d)) & 1;
+                const real* src = nullptr;
+                int q = 0;
+                if (d > 1) {
+                    q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
+                    src = (d - 1 <= G) ? gl + (int64_t)LP * (N - (N >> (d - 2)))
+                                       : sl + LP * ((N >> G) - (N >> (d - 2)));
+                }
+                int qb = 0;
+                const uint32_t* bsrc = nullptr;
+                if (bit && d <= nb) {
+                    qb = (ptrB >> ((d - 1) * PB)) & (LP - 1);
+                    bsrc = bw + LP * ((N >> 5) - (N >> (d + 4)));
+                }
+                if (d < n - 3) {
+                    real* dst = (d <= G) ? gl + (int64_t)LP * (N - (N >> (d - 1)))
+                                         : sl + LP * ((N >> G) - (N >> (d - 1)));
+                    if (act) {
+                        for (int k = kk; k < sz; k += S) {
+                            real a, b;
+                            if (d == 1) {
+                                const int r = (int)(__brev((unsigned)k) >> (32 - n));
+                                a = y[r];
+                                b = y[r + 1];
+                            } else {
+                                a = src[k * LP + q];
+                                b = src[(k + sz) * LP + q];
+                            }
+                            real v;
+                            if (bit) {
+                                uint32_t ub;
+                                if (d <= nb) ub = (bsrc[(k >> 5) * LP + qb] >> (k & 31)) & 1u;
+                                else ub = (small >> (32 - 2 * sz + k)) & 1u;
+                                v = pcl_fast<real>::g(a, b, ub);
+                            } else {
+                                v = pcl_math<real>::f(a, b);
+                            }
+                            dst[k * LP + p] = v;
+                        }
+                        ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                    }
+                    __syncwarp();
+                } else if (act) {                 // d == n-3: sz == 8, straight into registers
+#pragma unroll
+                    for (int t = 0; t < E3; t++) {
+                        const int k = kk + S * t;
+                        if (k < 8) {
+                            real a, b;
+                            if (d == 1) {
+                                const int r = (int)(__brev((unsigned)k) >> (32 - n));
+                                a = y[r];
+                                b = y[r + 1];
+                            } else {
+                                a = src[k * LP + q];
+                                b = src[(k + 8) * LP + q];
+                            }
+                            if (bit) {
+                                uint32_t ub;
+                                if (d <= nb) ub = (bsrc[qb] >> k) & 1u;      // k < 32: word 0
+                                else ub = (small >> (16 + k)) & 1u;
+                                R3[t] = pcl_fast<real>::g(a, b, ub);
+                            } else {
+                                R3[t] = pcl_math<real>::f(a, b);
+                            }
+                        }
+                    }
+                }
+            }
+            // all borrowed source arrays have been read: order before later overwrites
+            __syncwarp();
+
+            // ---- the 8 leaves of the block, fully unrolled --------------------------------
+            real R2[E2], R1[E1];
+#pragma unroll
+            for (int t = 0; t < E2; t++) R2[t] = (real)0;
+#pragma unroll
+            for (int t = 0; t < E1; t++) R1[t] = (real)0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int i = i0 + j;
+                const bool frozen = (fz8 >> j) & 1u;
+                // heights to recompute: j == 0 -> 2,1,0; else ctz(j) .. 0
+                if (j == 0 || j == 4) pcl_block_stage<LP, S, 4, real>(R2, R3, j == 4, small, kk, lane);
+                if ((j & 1) == 0) pcl_block_stage<LP, S, 2, real>(R1, R2, (j & 2) != 0, small, kk, lane);
+                real x;
+                pcl_block_stage<LP, S, 1, real>(&x, R1, (j & 1) != 0, small, kk, lane);
+                if (S > 1) x = pcl_shfl_real<real>(x, p);          // lane p is sub-lane 0 of the path
+                if (!act) x = (real)0;
+
+                // ---- leaf decision (polar_scl.cuh for the rules) -------------------------
+                const real ax = fabs(x);
+                const bool hard = !(x >= (real)0);
+                uint32_t u = 0;
+                int parent = p;
+                if (LP == 1) {
+                    u = frozen ? 0u : (hard ? 1u : 0u);
+                    if (P.want_pm) {
+                        const double sp = (double)pcl_fast<real>::softplus_neg_abs(ax);
+                        pm -= ((u != (uint32_t)hard) ? (double)ax : 0.0) + sp;
+                    }
+                } else if (frozen) {
+                    if (act) {
+                        const double sp = (double)pcl_fast<real>::softplus_neg_abs(ax);
+                        pm -= (hard ? (double)ax : 0.0) + sp;
+                    }
+                } else {
+                    double m0 = NEG_INF, m1 = NEG_INF;
+                    if (act) {
+                        const double sp = (double)pcl_fast<real>::softplus_neg_abs(ax);
+                        const double base = pm - sp;
+                        m0 = hard ? base - (double)ax : base;
+                        m1 = hard ? base : base - (double)ax;
+                    }
+                    if (kk == 0) { cm[p] = m0; cm[LP + p] = m1; }
+                    __syncwarp();
+                    const int ns = (2 * nact < L) ? 2 * nact : L;
+                    for (int c = lane; c < 2 * LP; c += 32) {
+                        const double mc = cm[c];
+                        int rank = 0;
+#pragma unroll
+                        for (int jj = 0; jj < 2 * LP; jj++) {
+                            const double mj = cm[jj];
+                            rank += (mj > mc) || (mj == mc && jj < c);
+                        }
+                        if (rank < ns) { sel[rank] = c; newpm[rank] = mc; }
+                    }
+                    __syncwarp();
+                    act = p < ns;
+                    if (act) {
+                        const int c = sel[p];
+                        parent = c & (LP - 1);
+                        u = (uint32_t)(c >> PB);
+                        pm = newpm[p];
+                    } else {
+                        pm = NEG_INF;
+                    }
+                    nact = ns;
+                    const int srcl = (lane & ~(LP - 1)) | parent;
+                    ptrL = __shfl_sync(PCL_FULL_MASK, ptrL, srcl);
+                    ptrB = __shfl_sync(PCL_FULL_MASK, ptrB, srcl);
+                    small = __shfl_sync(PCL_FULL_MASK, small, srcl);
+                    // registers still needed by later leaves of this block follow the path
+                    if (j < 4) {
+#pragma unroll
+                        for (int t = 0; t < E3; t++) R3[t] = pcl_shfl_real<real>(R3[t], srcl);
+                    }
+                    if ((j & 3) < 2) {
+#pragma unroll
+                        for (int t = 0; t < E2; t++) R2[t] = pcl_shfl_real<real>(R2[t], srcl);
+                    }
+                    if ((j & 1) == 0) {
+#pragma unroll
+                        for (int t = 0; t < E1; t++) R1[t] = pcl_shfl_real<real>(R1[t], srcl);
+                    }
+                    __syncwarp();
+                }
+                if (P.dbg_leaf != nullptr && kk == 0) {
+                    P.dbg_leaf[(f * N + i) * LP + p] = x;
+                    P.dbg_parent[(f * N + i) * LP + p] = (uint8_t)parent;
+                }
+
+                // ---- partial sums: fields of sizes 1, 2, 4 at bits 30, 28, 24 ------------
+                if ((j & 1) == 0) {
+                    small = pcl_bfi(small, u, 30, 1);
+                } else {
+                    const uint32_t c2 = (((small >> 30) & 1u) ^ u) | (u << 1);
+                    if ((j & 2) == 0) {
+                        small = pcl_bfi(small, c2, 28, 2);
+                    } else {
+                        const uint32_t c4 = (((small >> 28) & 3u) ^ c2) | (c2 << 2);
+                        if (j == 3) {
+                            small = pcl_bfi(small, c4, 24, 4);
+                        } else if (blk == NB - 1) {
+                            ulast = u;               // last leaf: the fields stay as they are
+                        } else {
+                            // block complete: fold upwards while the node is a right child
+                            uint32_t c = (((small >> 24) & 15u) ^ c4) | (c4 << 4);
+                            int s = 8, tt = blk;
+                            while ((tt & 1) && s < 32) {
+                                const uint32_t left = pcl_bfe(small, 32 - 2 * s, s);
+                                c = (left ^ c) | (c << s);
+                                s <<= 1;
+                                tt >>= 1;
+                            }
+                            if (!(tt & 1)) {
+                                if (s < 32) {
+                                    small = pcl_bfi(small, c, 32 - 2 * s, s);
+                                } else {
+                                    const int d = n - 5;
+                                    if (act) {
+                                        if (kk == 0) bw[LP * ((N >> 5) - (N >> (d + 4))) + p] = c;
+                                        ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                                    }
+                                    __syncwarp();
+                                }
+                            } else {
+                                const int cto = __ffs(~i) - 1;
+                                const int d = n - cto;
+                                const int Wd = N >> (d + 5);
+                                uint32_t* dest = bw + LP * ((N >> 5) - (N >> (d + 4)));
+                                if (act && kk == 0) dest[(Wd - 1) * LP + p] = c;
+                                __syncwarp();
+                                for (int l = n - 5; l > d; l--) {
+                                    const int w = N >> (l + 5);
+                                    const int ql = (ptrB >> ((l - 1) * PB)) & (LP - 1);
+                                    const uint32_t* lsrc = bw + LP * ((N >> 5) - (N >> (l + 4)));
+                                    if (act)
+                                        for (int jw = kk; jw < w; jw += S)
+                                            dest[(Wd - 2 * w + jw) * LP + p] =
+                                                lsrc[jw * LP + ql] ^ dest[(Wd - w + jw) * LP + p];
+                                    __syncwarp();
+                                }
+                                if (act) ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- final selection and output: identical to the generic kernel -------------------
+        int best = 0;
+        if (LP > 1) {
+            if (kk == 0) newpm[p] = pm;
+            __syncwarp();
+            double bm = newpm[0];
+            for (int q = 1; q < LP; q++) {
+                const double v = newpm[q];
+                if (v > bm) { bm = v; best = q; }
+            }
+        }
+        if (P.pm_out != nullptr && kk == 0 && p < L) P.pm_out[f * L + p] = pm;
+
+        const int nslots = P.use_crc ? nact : 1;
+        for (int sidx = 0; sidx < nslots; sidx++) {
+            const int slot = P.use_crc ? sidx : best;
+            uint32_t* U = uw + (P.use_crc ? sidx * NW : 0);
+            const uint32_t pB = __shfl_sync(PCL_FULL_MASK, ptrB, slot);
+            const uint32_t sm = __shfl_sync(PCL_FULL_MASK, small, slot);
+            const uint32_t ul = __shfl_sync(PCL_FULL_MASK, ulast, slot);
+            for (int w = lane; w < NW; w += 32) {
+                uint32_t v;
+                if (w == NW - 1) {
+                    v = pcl_bfi(sm, ul, 31, 1);
+                    v ^= (v >> 1) & 0x15555555u;
+                    v ^= (v >> 2) & 0x03333333u;
+                    v ^= (v >> 4) & 0x000F0F0Fu;
+                    v ^= (v >> 8) & 0x000000FFu;
+                } else {
+                    const int r = NW - w;
+                    const int Wl = 1 << (31 - __clz(r - 1));
+                    const int l = (31 - __clz(NW)) - (31 - __clz(Wl));
+                    const int jw = w - (NW - 2 * Wl);
+                    v = bw[LP * ((N >> 5) - (N >> (l + 4))) + jw * LP + ((pB >> ((l - 1) * PB)) & (LP - 1))];
+                    v ^= (v >> 1) & 0x55555555u;
+                    v ^= (v >> 2) & 0x33333333u;
+                    v ^= (v >> 4) & 0x0F0F0F0Fu;
+                    v ^= (v >> 8) & 0x00FF00FFu;
+                    v ^= (v >> 16) & 0x0000FFFFu;
+                }
+                U[w] = v;
+            }
+            __syncwarp();
+            for (int t = 1; t < NW; t <<= 1) {
+                for (int w = lane; w < NW - 1; w += 32) {
+                    const int r = NW - w;
+                    const int Wl = 1 << (31 - __clz(r - 1));
+                    const int jw = w - (NW - 2 * Wl);
+                    if (t < Wl && (jw & t) == 0) U[w] ^= U[w + t];
+                }
+                __syncwarp();
+            }
+        }
+
+        if (P.use_crc) {
+            bool pass = false;
+            if (kk == 0 && p < nact) {
+                const uint32_t* U = uw + p * NW;
+                const uint32_t top = 1u << (P.crc_len - 1);
+                const uint32_t msk = (P.crc_len >= 32) ? 0xffffffffu : ((1u << P.crc_len) - 1u);
+                uint32_t reg = 0;
+                for (int k = 0; k < K; k++) {
+                    const int pos = (int)P.info_pos[k] + shift;
+                    const uint32_t b = (U[pos >> 5] >> (pos & 31)) & 1u;
+                    reg ^= b << (P.crc_len - 1);
+                    reg = (reg & top) ? ((reg << 1) ^ P.crc_poly) : (reg << 1);
+                    reg &= msk;
+                }
+                pass = (reg == 0);
+            }
+            const unsigned pmask = __ballot_sync(PCL_FULL_MASK, pass);
+            if (pmask != 0) {
+                int bsel = -1;
+                double bm = 0;
+                for (int q = 0; q < nact; q++) {
+                    if (!((pmask >> q) & 1u)) continue;
+                    const double v = newpm[q];
+                    if (bsel < 0 || v > bm) { bm = v; bsel = q; }
+                }
+                best = bsel;
+            }
+        }
+        {
+            const uint32_t* U = uw + (P.use_crc ? best * NW : 0);
+            uint8_t* out = P.bits + f * K;
+            for (int k = lane; k < K; k += 32) {
+                const int pos = (int)P.info_pos[k] + shift;
+                out[k] = (uint8_t)((U[pos >> 5] >> (pos & 31)) & 1u);
+            }
+        }
+        __syncwarp();
+    }
+}

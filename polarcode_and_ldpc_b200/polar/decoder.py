@@ -111,10 +111,11 @@ class _PolarBase:
         return bit_reverse_permutation(self.n)
 
     def launch_info(self) -> dict:
-        g, b, s, lv = (ctypes.c_int() for _ in range(4))
+        g, b, s, lv, fa = (ctypes.c_int() for _ in range(5))
         _native.check(_native.lib().pcl_polar_launch_info(self._h, ctypes.byref(g), ctypes.byref(b),
-                                                          ctypes.byref(s), ctypes.byref(lv)))
-        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "global_levels": lv.value}
+                                                          ctypes.byref(s), ctypes.byref(lv), ctypes.byref(fa)))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "global_levels": lv.value,
+                "kernel": "polar_scl_fast_kernel" if fa.value else "polar_scl_kernel"}
 
     def decode_batch_host(self, llr_host, bits_host=None):
         """C-ABI host-buffer path: llr_host is a CPU tensor/array [F, N] in the compute

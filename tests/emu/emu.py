@@ -61,6 +61,9 @@ def polar_decode(N, K, L, frozen_bits, llr, dtype="f64", want_pm=False, want_lea
         llr = np.ascontiguousarray(np.atleast_2d(llr), dtype=rt)
         F = llr.shape[0]
         LP = L_.pcl_polar_lp(h)
+        fa = ctypes.c_int()
+        L_.pcl_polar_launch_info(h, None, None, None, None, ctypes.byref(fa))
+        polar_decode.last_fast = fa.value
         bits = np.full((F, K), 7, dtype=np.uint8)
         pm = np.zeros((F, L), dtype=np.float64) if want_pm else None
         leaf = np.zeros((F, N, LP), dtype=rt) if want_leaf else None

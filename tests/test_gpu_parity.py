@@ -330,3 +330,25 @@ def test_count_errors_and_counters():
     c.add(1, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
     c.allreduce()
     assert c.t[1, 0].item() == int(flip.sum()) and c.t[0].sum().item() == 0
+
+
+def test_generic_kernel_fallback_matches(golden_dir):
+    """PCL_POLAR_GENERIC=1 forces the all-shared-memory kernel that serves the (N, L) outside
+    the fast kernel's limits; it must give the same answers."""
+    os.environ["PCL_POLAR_GENERIC"] = "1"
+    try:
+        g = _g(golden_dir, "polar_scl.npz")
+        for ci in range(int(g["ncases"])):
+            N, L, fz, llr = int(g[f"c{ci}_N"]), int(g[f"c{ci}_L"]), g[f"c{ci}_frozen"], g[f"c{ci}_llr"]
+            dec = P.SCLDecoder(N, N - len(fz), list_size=L, frozen_bits=fz, dtype="float64")
+            assert dec.launch_info()["kernel"] == "polar_scl_kernel"
+            assert np.array_equal(dec.decode_batch(llr), g[f"c{ci}_bits"]), f"generic SCL case {ci}"
+        N, K = 1024, 512
+        frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+        _, llr = _polar_frames(N, K, frozen, 1024, 0.0, 21)
+        ref = oracle.polar_scl(N, 8, frozen, llr, nthreads=8)
+        assert np.array_equal(P.SCLDecoder(N, K, 8, frozen, dtype="float32").decode_batch(llr), ref)
+    finally:
+        os.environ.pop("PCL_POLAR_GENERIC")
+    assert P.SCLDecoder(1024, 512, 8, P.bhattacharyya_frozen_set(1024, 512, 2.0)).launch_info()["kernel"] == \
+        "polar_scl_fast_kernel"

@@ -96,15 +96,20 @@ def test_shard_range_partitions():
 
 
 # ---- kernel logic through the emulator (same .cuh sources as the CUDA build) ----
+@pytest.mark.parametrize("generic", [0, 1])
 @pytest.mark.parametrize("reverse", [False, True])
-def test_emu_polar_golden(golden_dir, reverse):
+def test_emu_polar_golden(golden_dir, reverse, generic):
+    """generic=1 forces the all-shared-memory kernel (polar_scl.cuh); 0 lets the library pick
+    the register-resident-bottom kernel (polar_scl_fast.cuh) wherever it applies (N >= 16)."""
+    env = {"PCL_POLAR_GENERIC": generic}
     g = np.load(os.path.join(golden_dir, "polar_scl.npz"))
     for ci in range(int(g["ncases"])):
         N, L, fz, llr = int(g[f"c{ci}_N"]), int(g[f"c{ci}_L"]), g[f"c{ci}_frozen"], g[f"c{ci}_llr"]
         if N > 256:
             continue
         bits, pm, (leaf, par) = emu.polar_decode(N, N - len(fz), L, fz, llr[:3], "f64", want_pm=True,
-                                                 want_leaf=True, reverse=reverse)
+                                                 want_leaf=True, reverse=reverse, env=env)
+        assert emu.polar_decode.last_fast == (0 if generic or N < 16 else 1)
         assert np.array_equal(bits, g[f"c{ci}_bits"][:3]), f"case {ci}"
         ref = g[f"c{ci}_pm"][:3]
         fin = np.isfinite(ref)
@@ -115,7 +120,7 @@ def test_emu_polar_golden(golden_dir, reverse):
         if N > 256:
             continue
         for dt in ("f64", "f32"):
-            bits = emu.polar_decode(N, N - len(fz), 1, fz, llr[:3], dt, reverse=reverse)
+            bits = emu.polar_decode(N, N - len(fz), 1, fz, llr[:3], dt, reverse=reverse, env=env)
             assert np.array_equal(bits, g[f"c{ci}_bits"][:3]), f"SC case {ci} {dt}"
 
 
@@ -127,10 +132,14 @@ def test_emu_polar_global_levels_and_crc():
     np.random.seed(2)
     llr = P.AWGNChannel(1.0).transmit_batch(enc.encode_batch(rng.integers(0, 2, size=(6, enc.K_data))))
     ref = oracle.polar_scl(N, L, fz, llr)
-    for G in (0, 1, 3, 6):
-        assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, "f64", env={"PCL_POLAR_G": G}), ref)
-    ref_crc = oracle.polar_scl(N, L, fz, llr, use_crc=True)
-    assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, "f64", crc=(0x1D, 8)), ref_crc)
+    for generic in (0, 1):
+        for G in (0, 1, 3, 6):
+            env = {"PCL_POLAR_G": G, "PCL_POLAR_GENERIC": generic}
+            assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, "f64", env=env), ref)
+            assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, "f32", env=env), ref)
+        ref_crc = oracle.polar_scl(N, L, fz, llr, use_crc=True)
+        assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, "f64", crc=(0x1D, 8),
+                                               env={"PCL_POLAR_GENERIC": generic}), ref_crc)
 
 
 def test_emu_ldpc_golden(golden_dir):
