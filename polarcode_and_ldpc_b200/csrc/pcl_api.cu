@@ -239,7 +239,7 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     h->fast = (n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 &&
                env_int("PCL_POLAR_GENERIC", 0) == 0) ? 1 : 0;
     const int gmax = h->fast ? n - 4 : n - 1;
-    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", 9216);
+    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", 7168);
     int G = env_int("PCL_POLAR_G", -1);
     if (G < 0) {
         for (G = 0; G < gmax; G++) {

@@ -91,23 +91,32 @@ PCL_DEVICE void pcl_block_stage(real* dst, const real* src, bool is_g, uint32_t 
 #pragma unroll
         for (int t = 0; t < CNT; t++) {
             const real a = src[t], b = src[t + CNT];
-            if (is_g) {
-                const uint32_t ub = (small >> (32 - 2 * Z + kk + S * t)) & 1u;
-                dst[t] = pcl_fast<real>::g(a, b, ub);
-            } else {
-                dst[t] = pcl_math<real>::f(a, b);
-            }
+            const uint32_t ub = (small >> (32 - 2 * Z + kk + S * t)) & 1u;
+            const real vg = pcl_fast<real>::g(a, b, ub);
+            const real vf = pcl_math<real>::f(a, b);
+            dst[t] = is_g ? vg : vf;
         }
     } else {
         const real a = src[0];
         const real b = pcl_shfl_real<real>(a, lane + Z * LP);     // element k + Z lives Z sub-lanes up
-        if (is_g) {
-            const uint32_t ub = (small >> ((32 - 2 * Z + kk) & 31)) & 1u;
-            dst[0] = pcl_fast<real>::g(a, b, ub);
-        } else {
-            dst[0] = pcl_math<real>::f(a, b);
-        }
+        const uint32_t ub = (small >> ((32 - 2 * Z + kk) & 31)) & 1u;
+        const real vg = pcl_fast<real>::g(a, b, ub);
+        const real vf = pcl_math<real>::f(a, b);
+        dst[0] = is_g ? vg : vf;
     }
+}
+
+// Prune keys.  fp64 (validation) build: exact total order (metric desc, candidate id asc),
+// the stable sort of decoder.py:306-307.  fp32 build: the candidate id replaces the lowest
+// mantissa bits of the (always negative) fp64 metric, so one compare decides both the
+// metric order and the reference's tie order; the perturbation is < 2^-46 relative.
+template <int NC, bool EXACT>
+PCL_DEVICE double pcl_prune_key(double m, int c)
+{
+    if (EXACT) return m;
+    long long b = __double_as_longlong(m);
+    b = (b & ~(long long)(NC - 1)) | (long long)c;
+    return __longlong_as_double(b);
 }
 
 template <int LP, typename real>
@@ -115,9 +124,16 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
 {
     constexpr int PB = pcl_log2<LP>::v;
     constexpr int S = 32 / LP;
+    constexpr int NC = 2 * LP;                   // prune candidates
+    constexpr bool EXACT = sizeof(real) == 8;
     constexpr int E3 = (8 >= S) ? 8 / S : 1;     // registers per lane for the size-8 level
     constexpr int E2 = (4 >= S) ? 4 / S : 1;
     constexpr int E1 = (2 >= S) ? 2 / S : 1;
+    // prune work split: lane (kk, p) owns candidate (kk & 1) * LP + p and compares it with
+    // the CH candidates of segment kk >> 1 (S >= 2); with S == 1 a lane owns two candidates.
+    constexpr int NSEG_RAW = (S >= 2) ? S / 2 : 1;
+    constexpr int NSEG = (NSEG_RAW > NC) ? NC : NSEG_RAW;
+    constexpr int CH = NC / NSEG;
     const PolarLayout& Y = P.lay;
     const int N = Y.N, n = Y.n, K = Y.K, L = Y.L, G = Y.G, NW = Y.NW, nb = Y.nb;
     const int lane = threadIdx.x & 31;
@@ -138,6 +154,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
     real* gl = P.scratch + (int64_t)(blockIdx.x * wpb + warp) * Y.scratch_per_warp;
 
     const double NEG_INF = -(double)pcl_math<real>::inf();
+    const double DEAD = -1.0e300;                 // key of an inactive slot (sorts last, stays finite)
 
     for (int64_t f = (int64_t)blockIdx.x * wpb + warp; f < P.F; f += (int64_t)gridDim.x * wpb) {
         const real* y = P.llr + f * N;
@@ -161,43 +178,46 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             for (int d = start; d <= n - 3; d++) {
                 const int sz = N >> d;
                 const int bit = (i0 >> (n - d)) & 1;
-                const real* src = nullptr;
-                int q = 0;
+                const real* src = nullptr;                     // + sub-lane and borrowed slot
                 if (d > 1) {
-                    q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
-                    src = (d - 1 <= G) ? gl + (int64_t)LP * (N - (N >> (d - 2)))
-                                       : sl + LP * ((N >> G) - (N >> (d - 2)));
+                    const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
+                    src = ((d - 1 <= G) ? gl + (int64_t)LP * (N - (N >> (d - 2)))
+                                        : sl + LP * ((N >> G) - (N >> (d - 2)))) + kk * LP + q;
                 }
-                int qb = 0;
                 const uint32_t* bsrc = nullptr;
-                if (bit && d <= nb) {
-                    qb = (ptrB >> ((d - 1) * PB)) & (LP - 1);
-                    bsrc = bw + LP * ((N >> 5) - (N >> (d + 4)));
-                }
+                if (bit && d <= nb)
+                    bsrc = bw + LP * ((N >> 5) - (N >> (d + 4))) + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
                 if (d < n - 3) {
-                    real* dst = (d <= G) ? gl + (int64_t)LP * (N - (N >> (d - 1)))
-                                         : sl + LP * ((N >> G) - (N >> (d - 1)));
+                    real* dst = ((d <= G) ? gl + (int64_t)LP * (N - (N >> (d - 1)))
+                                          : sl + LP * ((N >> G) - (N >> (d - 1)))) + kk * LP + p;
+                    // element k = kk + S t sits at word offset 32 t of the [k][slot] array
+                    const int hi = sz * LP;
                     if (act) {
-                        for (int k = kk; k < sz; k += S) {
-                            real a, b;
-                            if (d == 1) {
+                        if (d == 1) {
+                            for (int k = kk; k < sz; k += S) {
                                 const int r = (int)(__brev((unsigned)k) >> (32 - n));
-                                a = y[r];
-                                b = y[r + 1];
-                            } else {
-                                a = src[k * LP + q];
-                                b = src[(k + sz) * LP + q];
+                                const real a = y[r], b = y[r + 1];
+                                uint32_t ub = 0;
+                                if (bit) ub = (d <= nb) ? (bsrc[(k >> 5) * LP] >> (k & 31)) & 1u
+                                                        : (small >> (32 - 2 * sz + k)) & 1u;
+                                dst[(k - kk) * LP] = bit ? pcl_fast<real>::g(a, b, ub) : pcl_math<real>::f(a, b);
                             }
-                            real v;
-                            if (bit) {
-                                uint32_t ub;
-                                if (d <= nb) ub = (bsrc[(k >> 5) * LP + qb] >> (k & 31)) & 1u;
-                                else ub = (small >> (32 - 2 * sz + k)) & 1u;
-                                v = pcl_fast<real>::g(a, b, ub);
-                            } else {
-                                v = pcl_math<real>::f(a, b);
+                        } else if (!bit) {
+#pragma unroll 4
+                            for (int o = 0; o < hi; o += 32)
+                                if (o + kk * LP < hi) dst[o] = pcl_math<real>::f(src[o], src[o + hi]);
+                        } else if (d <= nb) {
+                            for (int k = kk; k < sz; k += S) {
+                                const int o = (k - kk) * LP;
+                                const uint32_t ub = (bsrc[(k >> 5) * LP] >> (k & 31)) & 1u;
+                                dst[o] = pcl_fast<real>::g(src[o], src[o + hi], ub);
                             }
-                            dst[k * LP + p] = v;
+                        } else {
+                            const uint32_t sm = small >> (32 - 2 * sz);
+                            for (int k = kk; k < sz; k += S) {
+                                const int o = (k - kk) * LP;
+                                dst[o] = pcl_fast<real>::g(src[o], src[o + hi], (sm >> k) & 1u);
+                            }
                         }
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
                     }
@@ -213,17 +233,12 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                                 a = y[r];
                                 b = y[r + 1];
                             } else {
-                                a = src[k * LP + q];
-                                b = src[(k + 8) * LP + q];
+                                a = src[32 * t];
+                                b = src[32 * t + 8 * LP];
                             }
-                            if (bit) {
-                                uint32_t ub;
-                                if (d <= nb) ub = (bsrc[qb] >> k) & 1u;      // k < 32: word 0
-                                else ub = (small >> (16 + k)) & 1u;
-                                R3[t] = pcl_fast<real>::g(a, b, ub);
-                            } else {
-                                R3[t] = pcl_math<real>::f(a, b);
-                            }
+                            const real vg = pcl_fast<real>::g(a, b, (small >> (16 + k)) & 1u);
+                            const real vf = pcl_math<real>::f(a, b);
+                            R3[t] = bit ? vg : vf;
                         }
                     }
                 }
@@ -231,18 +246,18 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             // all borrowed source arrays have been read: order before later overwrites
             __syncwarp();
 
-            // ---- the 8 leaves of the block, fully unrolled --------------------------------
+            // ---- the 8 leaves of the block (compact loop: the body must stay I-cache resident)
             real R2[E2], R1[E1];
 #pragma unroll
             for (int t = 0; t < E2; t++) R2[t] = (real)0;
 #pragma unroll
             for (int t = 0; t < E1; t++) R1[t] = (real)0;
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < 8; j++) {
                 const int i = i0 + j;
                 const bool frozen = (fz8 >> j) & 1u;
                 // heights to recompute: j == 0 -> 2,1,0; else ctz(j) .. 0
-                if (j == 0 || j == 4) pcl_block_stage<LP, S, 4, real>(R2, R3, j == 4, small, kk, lane);
+                if ((j & 3) == 0) pcl_block_stage<LP, S, 4, real>(R2, R3, (j & 4) != 0, small, kk, lane);
                 if ((j & 1) == 0) pcl_block_stage<LP, S, 2, real>(R1, R2, (j & 2) != 0, small, kk, lane);
                 real x;
                 pcl_block_stage<LP, S, 1, real>(&x, R1, (j & 1) != 0, small, kk, lane);
@@ -257,34 +272,61 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                 if (LP == 1) {
                     u = frozen ? 0u : (hard ? 1u : 0u);
                     if (P.want_pm) {
-                        const double sp = (double)pcl_fast<real>::softplus_neg_abs(ax);
-                        pm -= ((u != (uint32_t)hard) ? (double)ax : 0.0) + sp;
+                        const real pen = pcl_fast<real>::softplus_neg_abs(ax) + ((u != (uint32_t)hard) ? ax : (real)0);
+                        pm -= (double)pen;
                     }
                 } else if (frozen) {
-                    if (act) {
-                        const double sp = (double)pcl_fast<real>::softplus_neg_abs(ax);
-                        pm -= (hard ? (double)ax : 0.0) + sp;
-                    }
+                    const real pen = pcl_fast<real>::softplus_neg_abs(ax) + (hard ? ax : (real)0);
+                    if (act) pm -= (double)pen;
                 } else {
-                    double m0 = NEG_INF, m1 = NEG_INF;
-                    if (act) {
-                        const double sp = (double)pcl_fast<real>::softplus_neg_abs(ax);
-                        const double base = pm - sp;
-                        m0 = hard ? base - (double)ax : base;
-                        m1 = hard ? base : base - (double)ax;
-                    }
-                    if (kk == 0) { cm[p] = m0; cm[LP + p] = m1; }
-                    __syncwarp();
+                    const double base = pm - (double)pcl_fast<real>::softplus_neg_abs(ax);
+                    const double other = base - (double)ax;
                     const int ns = (2 * nact < L) ? 2 * nact : L;
-                    for (int c = lane; c < 2 * LP; c += 32) {
-                        const double mc = cm[c];
+                    if (S >= 2) {
+                        // own candidate: bit (kk & 1) of path p
+                        const int c = (kk & 1) * LP + p;
+                        const int seg = kk >> 1;
+                        double mc = ((kk & 1) != 0) == hard ? base : other;
+                        if (!act) mc = DEAD;
+                        const double key = pcl_prune_key<NC, EXACT>(mc, c);
+                        if (kk < 2) cm[c] = key;
+                        __syncwarp();
                         int rank = 0;
+                        if (seg < NSEG) {
 #pragma unroll
-                        for (int jj = 0; jj < 2 * LP; jj++) {
-                            const double mj = cm[jj];
-                            rank += (mj > mc) || (mj == mc && jj < c);
+                            for (int e = 0; e < CH; e++) {
+                                const int jj = seg * CH + e;
+                                const double kj = cm[jj];
+                                if (EXACT) rank += (kj > key) || (kj == key && jj < c);
+                                else rank += (kj > key);
+                            }
                         }
-                        if (rank < ns) { sel[rank] = c; newpm[rank] = mc; }
+#pragma unroll
+                        for (int o = 1; o < NSEG; o <<= 1) rank += __shfl_xor_sync(PCL_FULL_MASK, rank, 2 * LP * o);
+                        if (kk < 2 && rank < ns) { sel[rank] = c; newpm[rank] = mc; }
+                    } else {
+                        double mca = hard ? other : base;             // bit 0
+                        double mcb = hard ? base : other;             // bit 1
+                        if (!act) { mca = DEAD; mcb = DEAD; }
+                        const double ka = pcl_prune_key<NC, EXACT>(mca, p);
+                        const double kb = pcl_prune_key<NC, EXACT>(mcb, LP + p);
+                        cm[p] = ka;
+                        cm[LP + p] = kb;
+                        __syncwarp();
+                        int ra = 0, rb = 0;
+#pragma unroll 8
+                        for (int jj = 0; jj < NC; jj++) {
+                            const double kj = cm[jj];
+                            if (EXACT) {
+                                ra += (kj > ka) || (kj == ka && jj < p);
+                                rb += (kj > kb) || (kj == kb && jj < LP + p);
+                            } else {
+                                ra += (kj > ka);
+                                rb += (kj > kb);
+                            }
+                        }
+                        if (ra < ns) { sel[ra] = p; newpm[ra] = mca; }
+                        if (rb < ns) { sel[rb] = LP + p; newpm[rb] = mcb; }
                     }
                     __syncwarp();
                     act = p < ns;
