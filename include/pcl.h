@@ -72,8 +72,9 @@ int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8
                           void* stream);
 int pcl_polar_lp(const pcl_polar_t* h);
 /* Launch geometry of the last decode (for gpu_launches / occupancy reporting): grid, block,
- * dynamic shared memory, number of tree levels kept in the L2 scratch, and whether the
- * register-resident-bottom kernel (1) or the generic kernel (0) is in use. */
+ * dynamic shared memory, number of tree levels kept in the L2 scratch, and the kernel in use:
+ * 0 = generic kernel, S > 0 = register-resident-bottom kernel with S lanes per path
+ * (32 / (LP * S) frames per warp). */
 int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
                           int* fast);
 

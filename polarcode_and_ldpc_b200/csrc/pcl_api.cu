@@ -105,6 +105,7 @@ struct pcl_polar {
     int wpb, grid_max, smem_bytes;
     int last_grid = 0;
     int fast = 0;               // register-resident tree bottom (polar_scl_fast.cuh)
+    int S = 1, fpw = 1;         // fast kernel: lanes per path, frames per warp
     // host-buffer pipeline
     void* d_llr[PCL_NSTAGE] = {nullptr, nullptr};
     uint8_t* d_bits[PCL_NSTAGE] = {nullptr, nullptr};
@@ -116,79 +117,81 @@ struct pcl_polar {
 
 static size_t real_size(int dtype) { return dtype == PCL_F64 ? 8 : 4; }
 
-static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int rsz, bool crc, bool fast = false)
+static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int rsz, bool crc, bool fast = false,
+                         int fpw = 1)
 {
+    // `cols` = (frame, slot) columns a warp carries: LP for the generic kernel, LP * fpw for the fast one
+    const int cols = LP * fpw;
     Y.N = N; Y.n = ilog2i(N); Y.K = K; Y.L = L; Y.G = G;
     Y.NW = N >= 32 ? N / 32 : 1;
     Y.nb = Y.n > 5 ? Y.n - 5 : 0;
-    Y.uw_slots = crc ? LP : 1;
+    Y.uw_slots = crc ? cols : fpw;
     int off = 0;
-    Y.off_cm = off;     off += 2 * LP * 8;
-    Y.off_newpm = off;  off += LP * 8;
+    Y.off_cm = off;     off += 2 * cols * 8;
+    Y.off_newpm = off;  off += cols * 8;
     // generic kernel keeps levels G+1 .. n-1 in shared memory, the fast one G+1 .. n-4
-    int llr_vals = fast ? ((G >= Y.n - 4) ? 0 : LP * ((N >> G) - 16))
-                        : ((G >= Y.n - 1) ? 0 : LP * ((N >> G) - 2));
+    int llr_vals = fast ? ((G >= Y.n - 4) ? 0 : cols * ((N >> G) - 16))
+                        : ((G >= Y.n - 1) ? 0 : cols * ((N >> G) - 2));
     Y.off_llr = off;    off += align_up(llr_vals * rsz, 8);
-    Y.off_sel = off;    off += LP * 4;
-    Y.off_bw = off;     off += LP * (N >= 64 ? (N / 32 - 1) : 0) * 4;
+    Y.off_sel = off;    off += cols * 4;
+    Y.off_bw = off;     off += cols * (N >= 64 ? (N / 32 - 1) : 0) * 4;
     Y.off_uw = off;     off += Y.uw_slots * Y.NW * 4;
     Y.warp_bytes = align_up(off, 16);
-    Y.scratch_per_warp = (int64_t)LP * (N - (N >> G));
+    Y.scratch_per_warp = (int64_t)cols * (N - (N >> G));
 }
 
-template <int LP, typename real>
-static int polar_launch_t(pcl_polar* h, const PolarParams<real>& P, int grid, void* stream)
+// Kernel variants.  Generic: one frame per warp, every level in shared memory.  Fast: S lanes
+// per path, 32 / (LP * S) frames per warp (polar_scl_fast.cuh).
+#define PCL_POLAR_FAST_VARIANTS(X) \
+    X(1, 1) X(1, 2) X(2, 1) X(2, 2) X(4, 1) X(4, 2) X(8, 1) X(8, 2) X(8, 4) X(16, 1) X(16, 2) X(32, 1)
+
+static bool polar_fast_variant_exists(int LP, int S)
 {
-    (void)stream;
+#define X(lp, s) if (LP == lp && S == s) return true;
+    PCL_POLAR_FAST_VARIANTS(X)
+#undef X
+    return false;
+}
+
+template <typename real, typename Fn>
+static int polar_with_kernel(pcl_polar* h, Fn&& fn)
+{
     if (h->fast) {
-        auto kern = polar_scl_fast_kernel<LP, real>;
-        PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+#define X(lp, s) if (h->LP == lp && h->S == s) return fn(polar_scl_fast_kernel<lp, s, real>);
+        PCL_POLAR_FAST_VARIANTS(X)
+#undef X
     } else {
-        auto kern = polar_scl_kernel<LP, real>;
-        PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+        switch (h->LP) {
+            case 1: return fn(polar_scl_kernel<1, real>);
+            case 2: return fn(polar_scl_kernel<2, real>);
+            case 4: return fn(polar_scl_kernel<4, real>);
+            case 8: return fn(polar_scl_kernel<8, real>);
+            case 16: return fn(polar_scl_kernel<16, real>);
+            case 32: return fn(polar_scl_kernel<32, real>);
+        }
     }
-    return PCL_OK;
+    return fail(PCL_EUNSUPPORTED, "no kernel for list size %d", h->L);
 }
 
 template <typename real>
 static int polar_launch(pcl_polar* h, const PolarParams<real>& P, int grid, void* stream)
 {
-    switch (h->LP) {
-        case 1: return polar_launch_t<1, real>(h, P, grid, stream);
-        case 2: return polar_launch_t<2, real>(h, P, grid, stream);
-        case 4: return polar_launch_t<4, real>(h, P, grid, stream);
-        case 8: return polar_launch_t<8, real>(h, P, grid, stream);
-        case 16: return polar_launch_t<16, real>(h, P, grid, stream);
-        case 32: return polar_launch_t<32, real>(h, P, grid, stream);
-    }
-    return fail(PCL_EUNSUPPORTED, "list size %d not supported (max 32)", h->L);
+    (void)stream;
+    return polar_with_kernel<real>(h, [&](auto kern) -> int {
+        PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+        return PCL_OK;
+    });
 }
 
 #ifndef PCL_EMU
-template <int LP, typename real>
-static int polar_occ_t(int fast, int threads, int smem, int* bps)
-{
-    if (fast) {
-        CUDA_TRY(cudaFuncSetAttribute(polar_scl_fast_kernel<LP, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, polar_scl_fast_kernel<LP, real>, threads, smem));
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(polar_scl_kernel<LP, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, polar_scl_kernel<LP, real>, threads, smem));
-    }
-    return PCL_OK;
-}
 template <typename real>
-static int polar_occ(int LP, int fast, int threads, int smem, int* bps)
+static int polar_occ(pcl_polar* h, int threads, int smem, int* bps)
 {
-    switch (LP) {
-        case 1: return polar_occ_t<1, real>(fast, threads, smem, bps);
-        case 2: return polar_occ_t<2, real>(fast, threads, smem, bps);
-        case 4: return polar_occ_t<4, real>(fast, threads, smem, bps);
-        case 8: return polar_occ_t<8, real>(fast, threads, smem, bps);
-        case 16: return polar_occ_t<16, real>(fast, threads, smem, bps);
-        case 32: return polar_occ_t<32, real>(fast, threads, smem, bps);
-    }
-    return PCL_EUNSUPPORTED;
+    return polar_with_kernel<real>(h, [&](auto kern) -> int {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem));
+        return PCL_OK;
+    });
 }
 #endif
 
@@ -238,18 +241,25 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     while ((1 << pb) < LP) pb++;
     h->fast = (n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 &&
                env_int("PCL_POLAR_GENERIC", 0) == 0) ? 1 : 0;
+    h->S = 1; h->fpw = 1;
+    if (h->fast) {
+        int S = env_int("PCL_POLAR_S", LP >= 32 ? 1 : 2);
+        if (!polar_fast_variant_exists(LP, S)) S = LP >= 32 ? 1 : 2;
+        h->S = S;
+        h->fpw = 32 / (LP * S);
+    }
     const int gmax = h->fast ? n - 4 : n - 1;
-    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", 7168);
+    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 7168 * (h->fpw > 1 ? 2 : 1) : 9216);
     int G = env_int("PCL_POLAR_G", -1);
     if (G < 0) {
         for (G = 0; G < gmax; G++) {
-            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast);
+            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
             if (h->lay.warp_bytes <= budget) break;
         }
     }
     if (G > gmax) G = gmax;
     if (G < 0) G = 0;
-    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast);
+    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
     h->smem_bytes = h->lay.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
         delete h;
@@ -257,8 +267,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     }
     int bps = 1;
 #ifndef PCL_EMU
-    rc = (dtype == PCL_F64) ? polar_occ<double>(LP, h->fast, h->wpb * 32, h->smem_bytes, &bps)
-                            : polar_occ<float>(LP, h->fast, h->wpb * 32, h->smem_bytes, &bps);
+    rc = (dtype == PCL_F64) ? polar_occ<double>(h, h->wpb * 32, h->smem_bytes, &bps)
+                            : polar_occ<float>(h, h->wpb * 32, h->smem_bytes, &bps);
     if (rc) { delete h; return rc; }
     if (bps < 1) { delete h; return fail(PCL_ECUDA, "kernel does not fit on an SM"); }
 #endif
@@ -307,7 +317,7 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
                                      int* fast)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
-    if (fast) *fast = h->fast;
+    if (fast) *fast = h->fast ? h->S : 0;
     if (grid) *grid = h->last_grid;
     if (block) *block = h->wpb * 32;
     if (smem_bytes) *smem_bytes = h->smem_bytes;
@@ -334,7 +344,8 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
     P.use_crc = h->crc_len > 0;
     P.crc_len = h->crc_len;
     P.crc_poly = h->crc_poly;
-    int64_t need = (F + h->wpb - 1) / h->wpb;
+    const int64_t fpb = (int64_t)h->wpb * h->fpw;            // frames per block per pass
+    int64_t need = (F + fpb - 1) / fpb;
     int grid = (int)std::min<int64_t>(need, h->grid_max);
     h->last_grid = grid;
     int rc = polar_launch<real>(h, P, grid, stream);

@@ -82,27 +82,24 @@ PCL_DEVICE double pcl_shfl_real<double>(double v, int src)
 
 // One butterfly stage inside the register-resident block: level of size Z from the level
 // of size 2Z.  S lanes own a path; element k of a level of size z lives in lane (k % S),
-// register (k / S) when z >= S, and in lane k, register 0 when z < S.
-template <int LP, int S, int Z, typename real>
-PCL_DEVICE void pcl_block_stage(real* dst, const real* src, bool is_g, uint32_t small, int kk, int lane)
+// register (k / S) when z >= S, and in lane k, register 0 when z < S.  LPF = 32 / S is the
+// lane distance between consecutive sub-lanes of a path.
+template <int LPF, int S, int Z, bool IS_G, typename real>
+PCL_DEVICE void pcl_block_stage(real* dst, const real* src, uint32_t small, int kk, int lane)
 {
     if (Z >= S) {
         constexpr int CNT = (Z >= S) ? Z / S : 1;
 #pragma unroll
         for (int t = 0; t < CNT; t++) {
             const real a = src[t], b = src[t + CNT];
-            const uint32_t ub = (small >> (32 - 2 * Z + kk + S * t)) & 1u;
-            const real vg = pcl_fast<real>::g(a, b, ub);
-            const real vf = pcl_math<real>::f(a, b);
-            dst[t] = is_g ? vg : vf;
+            if (IS_G) dst[t] = pcl_fast<real>::g(a, b, (small >> (32 - 2 * Z + kk + S * t)) & 1u);
+            else dst[t] = pcl_math<real>::f(a, b);
         }
     } else {
         const real a = src[0];
-        const real b = pcl_shfl_real<real>(a, lane + Z * LP);     // element k + Z lives Z sub-lanes up
-        const uint32_t ub = (small >> ((32 - 2 * Z + kk) & 31)) & 1u;
-        const real vg = pcl_fast<real>::g(a, b, ub);
-        const real vf = pcl_math<real>::f(a, b);
-        dst[0] = is_g ? vg : vf;
+        const real b = pcl_shfl_real<real>(a, lane + Z * LPF);    // element k + Z lives Z sub-lanes up
+        if (IS_G) dst[0] = pcl_fast<real>::g(a, b, (small >> ((32 - 2 * Z + kk) & 31)) & 1u);
+        else dst[0] = pcl_math<real>::f(a, b);
     }
 }
 
@@ -119,17 +116,30 @@ PCL_DEVICE double pcl_prune_key(double m, int c)
     return __longlong_as_double(b);
 }
 
-template <int LP, typename real>
+template <bool EXACT>
+PCL_DEVICE int pcl_beats(double kj, double key, int jj, int c)
+{
+    if (EXACT) return (kj > key) || (kj == key && jj < c);
+    return kj > key;
+}
+
+// LP = list slots per frame (power of two), S = lanes per path; a warp decodes
+// FPW = 32 / (LP * S) frames side by side.  All frames of a warp follow the same
+// schedule (frozen pattern, number of live paths), so every branch stays warp-uniform and
+// the per-leaf bookkeeping instructions are shared by FPW frames.
+template <int LP, int S, typename real>
 __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P)
 {
     constexpr int PB = pcl_log2<LP>::v;
-    constexpr int S = 32 / LP;
-    constexpr int NC = 2 * LP;                   // prune candidates
+    constexpr int LPF = 32 / S;                  // columns = (frame, slot) pairs per warp
+    constexpr int CB = pcl_log2<LPF>::v;
+    constexpr int FPW = LPF / LP;                // frames per warp
+    constexpr int NC = 2 * LP;                   // prune candidates per frame
     constexpr bool EXACT = sizeof(real) == 8;
     constexpr int E3 = (8 >= S) ? 8 / S : 1;     // registers per lane for the size-8 level
     constexpr int E2 = (4 >= S) ? 4 / S : 1;
     constexpr int E1 = (2 >= S) ? 2 / S : 1;
-    // prune work split: lane (kk, p) owns candidate (kk & 1) * LP + p and compares it with
+    // prune work split: lane (kk, col) owns candidate (kk & 1) * LP + p and compares it with
     // the CH candidates of segment kk >> 1 (S >= 2); with S == 1 a lane owns two candidates.
     constexpr int NSEG_RAW = (S >= 2) ? S / 2 : 1;
     constexpr int NSEG = (NSEG_RAW > NC) ? NC : NSEG_RAW;
@@ -139,27 +149,32 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int p = lane & (LP - 1);
-    const int kk = lane >> PB;
+    const int col = lane & (LPF - 1);
+    const int kk = lane >> CB;
+    const int p = col & (LP - 1);
+    const int fr = col >> PB;
+    const int cbase = col - p;                    // first column of this lane's frame
     const int shift = (N < 32) ? 32 - N : 0;
     const int NB = N >> 3;
 
     unsigned char* wsm = pcl_dyn_smem() + (size_t)warp * Y.warp_bytes;
-    double* cm = (double*)(wsm + Y.off_cm);
-    double* newpm = (double*)(wsm + Y.off_newpm);
-    int* sel = (int*)(wsm + Y.off_sel);
-    real* sl = (real*)(wsm + Y.off_llr);          // levels G+1 .. n-4
-    uint32_t* bw = (uint32_t*)(wsm + Y.off_bw);   // big left levels 1 .. nb
+    double* cm = (double*)(wsm + Y.off_cm) + fr * NC;          // this frame's candidate keys
+    double* newpm = (double*)(wsm + Y.off_newpm) + cbase;
+    int* sel = (int*)(wsm + Y.off_sel) + cbase;
+    real* sl = (real*)(wsm + Y.off_llr);          // levels G+1 .. n-4, [k][col]
+    uint32_t* bw = (uint32_t*)(wsm + Y.off_bw);   // big left levels 1 .. nb, [w][col]
     uint32_t* uw = (uint32_t*)(wsm + Y.off_uw);   // final u words
     real* gl = P.scratch + (int64_t)(blockIdx.x * wpb + warp) * Y.scratch_per_warp;
 
     const double NEG_INF = -(double)pcl_math<real>::inf();
     const double DEAD = -1.0e300;                 // key of an inactive slot (sorts last, stays finite)
 
-    for (int64_t f = (int64_t)blockIdx.x * wpb + warp; f < P.F; f += (int64_t)gridDim.x * wpb) {
-        const real* y = P.llr + f * N;
+    for (int64_t f0 = ((int64_t)blockIdx.x * wpb + warp) * FPW; f0 < P.F; f0 += (int64_t)gridDim.x * wpb * FPW) {
+        const int64_t f = f0 + fr;
+        const bool valid = f < P.F;
+        const real* y = P.llr + (valid ? f : f0) * N;
         int nact = 1;
-        bool act = (p == 0);
+        bool act = (p == 0) && valid;
         double pm = act ? 0.0 : NEG_INF;
         uint32_t ptrL = 0, ptrB = 0;              // packed slot pointers: LLR levels / left levels
         uint32_t small = 0, ulast = 0;
@@ -178,44 +193,44 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             for (int d = start; d <= n - 3; d++) {
                 const int sz = N >> d;
                 const int bit = (i0 >> (n - d)) & 1;
-                const real* src = nullptr;                     // + sub-lane and borrowed slot
+                const real* src = nullptr;                     // + sub-lane and borrowed column
                 if (d > 1) {
                     const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
-                    src = ((d - 1 <= G) ? gl + (int64_t)LP * (N - (N >> (d - 2)))
-                                        : sl + LP * ((N >> G) - (N >> (d - 2)))) + kk * LP + q;
+                    src = ((d - 1 <= G) ? gl + (int64_t)LPF * (N - (N >> (d - 2)))
+                                        : sl + LPF * ((N >> G) - (N >> (d - 2)))) + kk * LPF + cbase + q;
                 }
                 const uint32_t* bsrc = nullptr;
                 if (bit && d <= nb)
-                    bsrc = bw + LP * ((N >> 5) - (N >> (d + 4))) + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
+                    bsrc = bw + LPF * ((N >> 5) - (N >> (d + 4))) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
                 if (d < n - 3) {
-                    real* dst = ((d <= G) ? gl + (int64_t)LP * (N - (N >> (d - 1)))
-                                          : sl + LP * ((N >> G) - (N >> (d - 1)))) + kk * LP + p;
-                    // element k = kk + S t sits at word offset 32 t of the [k][slot] array
-                    const int hi = sz * LP;
+                    real* dst = ((d <= G) ? gl + (int64_t)LPF * (N - (N >> (d - 1)))
+                                          : sl + LPF * ((N >> G) - (N >> (d - 1)))) + kk * LPF + col;
+                    // element k = kk + S t sits at word offset 32 t of the [k][col] array
+                    const int hi = sz * LPF;
                     if (act) {
                         if (d == 1) {
                             for (int k = kk; k < sz; k += S) {
                                 const int r = (int)(__brev((unsigned)k) >> (32 - n));
                                 const real a = y[r], b = y[r + 1];
                                 uint32_t ub = 0;
-                                if (bit) ub = (d <= nb) ? (bsrc[(k >> 5) * LP] >> (k & 31)) & 1u
+                                if (bit) ub = (d <= nb) ? (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u
                                                         : (small >> (32 - 2 * sz + k)) & 1u;
-                                dst[(k - kk) * LP] = bit ? pcl_fast<real>::g(a, b, ub) : pcl_math<real>::f(a, b);
+                                dst[(k - kk) * LPF] = bit ? pcl_fast<real>::g(a, b, ub) : pcl_math<real>::f(a, b);
                             }
                         } else if (!bit) {
 #pragma unroll 4
                             for (int o = 0; o < hi; o += 32)
-                                if (o + kk * LP < hi) dst[o] = pcl_math<real>::f(src[o], src[o + hi]);
+                                if (o + kk * LPF < hi) dst[o] = pcl_math<real>::f(src[o], src[o + hi]);
                         } else if (d <= nb) {
                             for (int k = kk; k < sz; k += S) {
-                                const int o = (k - kk) * LP;
-                                const uint32_t ub = (bsrc[(k >> 5) * LP] >> (k & 31)) & 1u;
+                                const int o = (k - kk) * LPF;
+                                const uint32_t ub = (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u;
                                 dst[o] = pcl_fast<real>::g(src[o], src[o + hi], ub);
                             }
                         } else {
                             const uint32_t sm = small >> (32 - 2 * sz);
                             for (int k = kk; k < sz; k += S) {
-                                const int o = (k - kk) * LP;
+                                const int o = (k - kk) * LPF;
                                 dst[o] = pcl_fast<real>::g(src[o], src[o + hi], (sm >> k) & 1u);
                             }
                         }
@@ -234,7 +249,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                                 b = y[r + 1];
                             } else {
                                 a = src[32 * t];
-                                b = src[32 * t + 8 * LP];
+                                b = src[32 * t + 8 * LPF];
                             }
                             const real vg = pcl_fast<real>::g(a, b, (small >> (16 + k)) & 1u);
                             const real vf = pcl_math<real>::f(a, b);
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             // all borrowed source arrays have been read: order before later overwrites
             __syncwarp();
 
-            // ---- the 8 leaves of the block (compact loop: the body must stay I-cache resident)
+            // ---- the 8 leaves of the block (rolled: the body must stay I-cache resident) ----
             real R2[E2], R1[E1];
 #pragma unroll
             for (int t = 0; t < E2; t++) R2[t] = (real)0;
@@ -256,12 +271,21 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             for (int j = 0; j < 8; j++) {
                 const int i = i0 + j;
                 const bool frozen = (fz8 >> j) & 1u;
-                // heights to recompute: j == 0 -> 2,1,0; else ctz(j) .. 0
-                if ((j & 3) == 0) pcl_block_stage<LP, S, 4, real>(R2, R3, (j & 4) != 0, small, kk, lane);
-                if ((j & 1) == 0) pcl_block_stage<LP, S, 2, real>(R1, R2, (j & 2) != 0, small, kk, lane);
+                // heights to recompute: j == 0 -> 2,1,0; else ctz(j) .. 0; f or g per bit of j
                 real x;
-                pcl_block_stage<LP, S, 1, real>(&x, R1, (j & 1) != 0, small, kk, lane);
-                if (S > 1) x = pcl_shfl_real<real>(x, p);          // lane p is sub-lane 0 of the path
+                if (j & 1) {
+                    pcl_block_stage<LPF, S, 1, true, real>(&x, R1, small, kk, lane);
+                } else {
+                    if ((j & 2) == 0) {
+                        if (j & 4) pcl_block_stage<LPF, S, 4, true, real>(R2, R3, small, kk, lane);
+                        else pcl_block_stage<LPF, S, 4, false, real>(R2, R3, small, kk, lane);
+                        pcl_block_stage<LPF, S, 2, false, real>(R1, R2, small, kk, lane);
+                    } else {
+                        pcl_block_stage<LPF, S, 2, true, real>(R1, R2, small, kk, lane);
+                    }
+                    pcl_block_stage<LPF, S, 1, false, real>(&x, R1, small, kk, lane);
+                }
+                if (S > 1) x = pcl_shfl_real<real>(x, col);        // lane `col` is sub-lane 0 of the path
                 if (!act) x = (real)0;
 
                 // ---- leaf decision (polar_scl.cuh for the rules) -------------------------
@@ -269,16 +293,18 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                 const bool hard = !(x >= (real)0);
                 uint32_t u = 0;
                 int parent = p;
+                bool forked = false;
                 if (LP == 1) {
                     u = frozen ? 0u : (hard ? 1u : 0u);
                     if (P.want_pm) {
                         const real pen = pcl_fast<real>::softplus_neg_abs(ax) + ((u != (uint32_t)hard) ? ax : (real)0);
-                        pm -= (double)pen;
+                        if (act) pm -= (double)pen;
                     }
                 } else if (frozen) {
                     const real pen = pcl_fast<real>::softplus_neg_abs(ax) + (hard ? ax : (real)0);
                     if (act) pm -= (double)pen;
                 } else {
+                    forked = true;
                     const double base = pm - (double)pcl_fast<real>::softplus_neg_abs(ax);
                     const double other = base - (double)ax;
                     const int ns = (2 * nact < L) ? 2 * nact : L;
@@ -294,15 +320,10 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                         int rank = 0;
                         if (seg < NSEG) {
 #pragma unroll
-                            for (int e = 0; e < CH; e++) {
-                                const int jj = seg * CH + e;
-                                const double kj = cm[jj];
-                                if (EXACT) rank += (kj > key) || (kj == key && jj < c);
-                                else rank += (kj > key);
-                            }
+                            for (int e = 0; e < CH; e++) rank += pcl_beats<EXACT>(cm[seg * CH + e], key, seg * CH + e, c);
                         }
 #pragma unroll
-                        for (int o = 1; o < NSEG; o <<= 1) rank += __shfl_xor_sync(PCL_FULL_MASK, rank, 2 * LP * o);
+                        for (int o = 1; o < NSEG; o <<= 1) rank += __shfl_xor_sync(PCL_FULL_MASK, rank, 2 * LPF * o);
                         if (kk < 2 && rank < ns) { sel[rank] = c; newpm[rank] = mc; }
                     } else {
                         double mca = hard ? other : base;             // bit 0
@@ -317,33 +338,29 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
 #pragma unroll 8
                         for (int jj = 0; jj < NC; jj++) {
                             const double kj = cm[jj];
-                            if (EXACT) {
-                                ra += (kj > ka) || (kj == ka && jj < p);
-                                rb += (kj > kb) || (kj == kb && jj < LP + p);
-                            } else {
-                                ra += (kj > ka);
-                                rb += (kj > kb);
-                            }
+                            ra += pcl_beats<EXACT>(kj, ka, jj, p);
+                            rb += pcl_beats<EXACT>(kj, kb, jj, LP + p);
                         }
                         if (ra < ns) { sel[ra] = p; newpm[ra] = mca; }
                         if (rb < ns) { sel[rb] = LP + p; newpm[rb] = mcb; }
                     }
                     __syncwarp();
-                    act = p < ns;
-                    if (act) {
+                    act = (p < ns) && valid;
+                    if (p < ns) {
                         const int c = sel[p];
                         parent = c & (LP - 1);
                         u = (uint32_t)(c >> PB);
                         pm = newpm[p];
-                    } else {
-                        pm = NEG_INF;
                     }
+                    if (!act) pm = NEG_INF;
                     nact = ns;
+                }
+                if (forked) {
+                    // a survivor takes over its parent's pointer words and live registers
                     const int srcl = (lane & ~(LP - 1)) | parent;
                     ptrL = __shfl_sync(PCL_FULL_MASK, ptrL, srcl);
                     ptrB = __shfl_sync(PCL_FULL_MASK, ptrB, srcl);
                     small = __shfl_sync(PCL_FULL_MASK, small, srcl);
-                    // registers still needed by later leaves of this block follow the path
                     if (j < 4) {
 #pragma unroll
                         for (int t = 0; t < E3; t++) R3[t] = pcl_shfl_real<real>(R3[t], srcl);
@@ -358,22 +375,22 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                     }
                     __syncwarp();
                 }
-                if (P.dbg_leaf != nullptr && kk == 0) {
+                if (P.dbg_leaf != nullptr && kk == 0 && valid) {
                     P.dbg_leaf[(f * N + i) * LP + p] = x;
                     P.dbg_parent[(f * N + i) * LP + p] = (uint8_t)parent;
                 }
 
                 // ---- partial sums: fields of sizes 1, 2, 4 at bits 30, 28, 24 ------------
                 if ((j & 1) == 0) {
-                    small = pcl_bfi(small, u, 30, 1);
+                    small = (small & ~(1u << 30)) | (u << 30);
                 } else {
                     const uint32_t c2 = (((small >> 30) & 1u) ^ u) | (u << 1);
                     if ((j & 2) == 0) {
-                        small = pcl_bfi(small, c2, 28, 2);
+                        small = (small & ~(3u << 28)) | (c2 << 28);
                     } else {
                         const uint32_t c4 = (((small >> 28) & 3u) ^ c2) | (c2 << 2);
                         if (j == 3) {
-                            small = pcl_bfi(small, c4, 24, 4);
+                            small = (small & ~(15u << 24)) | (c4 << 24);
                         } else if (blk == NB - 1) {
                             ulast = u;               // last leaf: the fields stay as they are
                         } else {
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                                 } else {
                                     const int d = n - 5;
                                     if (act) {
-                                        if (kk == 0) bw[LP * ((N >> 5) - (N >> (d + 4))) + p] = c;
+                                        if (kk == 0) bw[LPF * ((N >> 5) - (N >> (d + 4))) + col] = c;
                                         ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
                                     }
                                     __syncwarp();
@@ -401,17 +418,17 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                                 const int cto = __ffs(~i) - 1;
                                 const int d = n - cto;
                                 const int Wd = N >> (d + 5);
-                                uint32_t* dest = bw + LP * ((N >> 5) - (N >> (d + 4)));
-                                if (act && kk == 0) dest[(Wd - 1) * LP + p] = c;
+                                uint32_t* dest = bw + LPF * ((N >> 5) - (N >> (d + 4)));
+                                if (act && kk == 0) dest[(Wd - 1) * LPF + col] = c;
                                 __syncwarp();
                                 for (int l = n - 5; l > d; l--) {
                                     const int w = N >> (l + 5);
-                                    const int ql = (ptrB >> ((l - 1) * PB)) & (LP - 1);
-                                    const uint32_t* lsrc = bw + LP * ((N >> 5) - (N >> (l + 4)));
+                                    const int ql = cbase + ((ptrB >> ((l - 1) * PB)) & (LP - 1));
+                                    const uint32_t* lsrc = bw + LPF * ((N >> 5) - (N >> (l + 4)));
                                     if (act)
                                         for (int jw = kk; jw < w; jw += S)
-                                            dest[(Wd - 2 * w + jw) * LP + p] =
-                                                lsrc[jw * LP + ql] ^ dest[(Wd - w + jw) * LP + p];
+                                            dest[(Wd - 2 * w + jw) * LPF + col] =
+                                                lsrc[jw * LPF + ql] ^ dest[(Wd - w + jw) * LPF + col];
                                     __syncwarp();
                                 }
                                 if (act) ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
@@ -422,7 +439,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             }
         }
 
-        // ---- final selection and output: identical to the generic kernel -------------------
+        // ---- final selection (decoder.py:259-262), per frame of the warp ------------------------
         int best = 0;
         if (LP > 1) {
             if (kk == 0) newpm[p] = pm;
@@ -430,56 +447,61 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             double bm = newpm[0];
             for (int q = 1; q < LP; q++) {
                 const double v = newpm[q];
-                if (v > bm) { bm = v; best = q; }
+                if (v > bm) { bm = v; best = q; }           // first maximum, like np.argmax
             }
         }
-        if (P.pm_out != nullptr && kk == 0 && p < L) P.pm_out[f * L + p] = pm;
+        if (P.pm_out != nullptr && kk == 0 && p < L && valid) P.pm_out[f * L + p] = pm;
 
         const int nslots = P.use_crc ? nact : 1;
-        for (int sidx = 0; sidx < nslots; sidx++) {
-            const int slot = P.use_crc ? sidx : best;
-            uint32_t* U = uw + (P.use_crc ? sidx * NW : 0);
-            const uint32_t pB = __shfl_sync(PCL_FULL_MASK, ptrB, slot);
-            const uint32_t sm = __shfl_sync(PCL_FULL_MASK, small, slot);
-            const uint32_t ul = __shfl_sync(PCL_FULL_MASK, ulast, slot);
-            for (int w = lane; w < NW; w += 32) {
-                uint32_t v;
-                if (w == NW - 1) {
-                    v = pcl_bfi(sm, ul, 31, 1);
-                    v ^= (v >> 1) & 0x15555555u;
-                    v ^= (v >> 2) & 0x03333333u;
-                    v ^= (v >> 4) & 0x000F0F0Fu;
-                    v ^= (v >> 8) & 0x000000FFu;
-                } else {
-                    const int r = NW - w;
-                    const int Wl = 1 << (31 - __clz(r - 1));
-                    const int l = (31 - __clz(NW)) - (31 - __clz(Wl));
-                    const int jw = w - (NW - 2 * Wl);
-                    v = bw[LP * ((N >> 5) - (N >> (l + 4))) + jw * LP + ((pB >> ((l - 1) * PB)) & (LP - 1))];
-                    v ^= (v >> 1) & 0x55555555u;
-                    v ^= (v >> 2) & 0x33333333u;
-                    v ^= (v >> 4) & 0x0F0F0F0Fu;
-                    v ^= (v >> 8) & 0x00FF00FFu;
-                    v ^= (v >> 16) & 0x0000FFFFu;
-                }
-                U[w] = v;
-            }
-            __syncwarp();
-            for (int t = 1; t < NW; t <<= 1) {
-                for (int w = lane; w < NW - 1; w += 32) {
-                    const int r = NW - w;
-                    const int Wl = 1 << (31 - __clz(r - 1));
-                    const int jw = w - (NW - 2 * Wl);
-                    if (t < Wl && (jw & t) == 0) U[w] ^= U[w + t];
+        for (int fq = 0; fq < FPW; fq++) {
+            const int fbest = __shfl_sync(PCL_FULL_MASK, best, fq * LP);
+            for (int sidx = 0; sidx < nslots; sidx++) {
+                const int slot = P.use_crc ? sidx : fbest;
+                uint32_t* U = uw + (P.use_crc ? (fq * LP + sidx) * NW : fq * NW);
+                const uint32_t pB = __shfl_sync(PCL_FULL_MASK, ptrB, fq * LP + slot);
+                const uint32_t sm = __shfl_sync(PCL_FULL_MASK, small, fq * LP + slot);
+                const uint32_t ul = __shfl_sync(PCL_FULL_MASK, ulast, fq * LP + slot);
+                for (int w = lane; w < NW; w += 32) {
+                    uint32_t v;
+                    if (w == NW - 1) {
+                        v = pcl_bfi(sm, ul, 31, 1);
+                        v ^= (v >> 1) & 0x15555555u;
+                        v ^= (v >> 2) & 0x03333333u;
+                        v ^= (v >> 4) & 0x000F0F0Fu;
+                        v ^= (v >> 8) & 0x000000FFu;
+                    } else {
+                        const int r = NW - w;
+                        const int Wl = 1 << (31 - __clz(r - 1));
+                        const int l = (31 - __clz(NW)) - (31 - __clz(Wl));
+                        const int jw = w - (NW - 2 * Wl);
+                        v = bw[LPF * ((N >> 5) - (N >> (l + 4))) + jw * LPF + fq * LP + ((pB >> ((l - 1) * PB)) & (LP - 1))];
+                        v ^= (v >> 1) & 0x55555555u;
+                        v ^= (v >> 2) & 0x33333333u;
+                        v ^= (v >> 4) & 0x0F0F0F0Fu;
+                        v ^= (v >> 8) & 0x00FF00FFu;
+                        v ^= (v >> 16) & 0x0000FFFFu;
+                    }
+                    U[w] = v;
                 }
                 __syncwarp();
+                for (int t = 1; t < NW; t <<= 1) {
+                    for (int w = lane; w < NW - 1; w += 32) {
+                        const int r = NW - w;
+                        const int Wl = 1 << (31 - __clz(r - 1));
+                        const int jw = w - (NW - 2 * Wl);
+                        if (t < Wl && (jw & t) == 0) U[w] ^= U[w + t];
+                    }
+                    __syncwarp();
+                }
             }
         }
 
         if (P.use_crc) {
+            // first path in (metric desc, slot asc) order whose info bits pass the CRC register
+            // test (src/polar/utils.py:128-163); else the best metric.
             bool pass = false;
-            if (kk == 0 && p < nact) {
-                const uint32_t* U = uw + p * NW;
+            if (kk == 0 && p < nact && valid) {
+                const uint32_t* U = uw + col * NW;
                 const uint32_t top = 1u << (P.crc_len - 1);
                 const uint32_t msk = (P.crc_len >= 32) ? 0xffffffffu : ((1u << P.crc_len) - 1u);
                 uint32_t reg = 0;
@@ -492,7 +514,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                 }
                 pass = (reg == 0);
             }
-            const unsigned pmask = __ballot_sync(PCL_FULL_MASK, pass);
+            const unsigned pmask = (__ballot_sync(PCL_FULL_MASK, pass) >> cbase) & ((LP >= 32) ? 0xffffffffu : ((1u << LP) - 1u));
             if (pmask != 0) {
                 int bsel = -1;
                 double bm = 0;
@@ -504,12 +526,15 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                 best = bsel;
             }
         }
-        {
-            const uint32_t* U = uw + (P.use_crc ? best * NW : 0);
-            uint8_t* out = P.bits + f * K;
-            for (int k = lane; k < K; k += 32) {
-                const int pos = (int)P.info_pos[k] + shift;
-                out[k] = (uint8_t)((U[pos >> 5] >> (pos & 31)) & 1u);
+        for (int fq = 0; fq < FPW; fq++) {   // decoded = u[info_bits] (decoder.py:70-71 / :260-262)
+            const int fbest = __shfl_sync(PCL_FULL_MASK, best, fq * LP);
+            if (f0 + fq < P.F) {
+                const uint32_t* U = uw + (P.use_crc ? (fq * LP + fbest) * NW : fq * NW);
+                uint8_t* out = P.bits + (f0 + fq) * K;
+                for (int k = lane; k < K; k += 32) {
+                    const int pos = (int)P.info_pos[k] + shift;
+                    out[k] = (uint8_t)((U[pos >> 5] >> (pos & 31)) & 1u);
+                }
             }
         }
         __syncwarp();

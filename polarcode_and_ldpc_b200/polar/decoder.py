@@ -115,7 +115,8 @@ class _PolarBase:
         _native.check(_native.lib().pcl_polar_launch_info(self._h, ctypes.byref(g), ctypes.byref(b),
                                                           ctypes.byref(s), ctypes.byref(lv), ctypes.byref(fa)))
         return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "global_levels": lv.value,
-                "kernel": "polar_scl_fast_kernel" if fa.value else "polar_scl_kernel"}
+                "kernel": "polar_scl_fast_kernel" if fa.value else "polar_scl_kernel",
+                "lanes_per_path": fa.value, "frames_per_warp": (32 // (self._LP * fa.value)) if fa.value else 1}
 
     def decode_batch_host(self, llr_host, bits_host=None):
         """C-ABI host-buffer path: llr_host is a CPU tensor/array [F, N] in the compute

@@ -109,7 +109,7 @@ def test_emu_polar_golden(golden_dir, reverse, generic):
             continue
         bits, pm, (leaf, par) = emu.polar_decode(N, N - len(fz), L, fz, llr[:3], "f64", want_pm=True,
                                                  want_leaf=True, reverse=reverse, env=env)
-        assert emu.polar_decode.last_fast == (0 if generic or N < 16 else 1)
+        assert (emu.polar_decode.last_fast > 0) == (not (generic or N < 16))
         assert np.array_equal(bits, g[f"c{ci}_bits"][:3]), f"case {ci}"
         ref = g[f"c{ci}_pm"][:3]
         fin = np.isfinite(ref)
