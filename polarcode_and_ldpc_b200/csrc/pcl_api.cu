@@ -130,6 +130,7 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
     Y.off_cm = off;     off += 2 * cols * 8;
     Y.off_newpm = off;  off += cols * 8;
     // generic kernel keeps levels G+1 .. n-1 in shared memory, the fast one G+1 .. n-4
+    // (the fast kernel never stores level 1, so its G is at least 1)
     int llr_vals = fast ? ((G >= Y.n - 4) ? 0 : cols * ((N >> G) - 16))
                         : ((G >= Y.n - 1) ? 0 : cols * ((N >> G) - 2));
     Y.off_llr = off;    off += align_up(llr_vals * rsz, 8);
@@ -137,7 +138,8 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
     Y.off_bw = off;     off += cols * (N >= 64 ? (N / 32 - 1) : 0) * 4;
     Y.off_uw = off;     off += Y.uw_slots * Y.NW * 4;
     Y.warp_bytes = align_up(off, 16);
-    Y.scratch_per_warp = (int64_t)cols * (N - (N >> G));
+    Y.scratch_per_warp = fast ? (int64_t)cols * ((N >> 1) - (N >> G))     // levels 2 .. G
+                              : (int64_t)cols * (N - (N >> G));           // levels 1 .. G
 }
 
 // Kernel variants.  Generic: one frame per warp, every level in shared memory.  Fast: S lanes
@@ -251,14 +253,15 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     const int gmax = h->fast ? n - 4 : n - 1;
     int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 7168 * (h->fpw > 1 ? 2 : 1) : 9216);
     int G = env_int("PCL_POLAR_G", -1);
+    const int gmin = h->fast ? 1 : 0;
     if (G < 0) {
-        for (G = 0; G < gmax; G++) {
+        for (G = gmin; G < gmax; G++) {
             polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
             if (h->lay.warp_bytes <= budget) break;
         }
     }
     if (G > gmax) G = gmax;
-    if (G < 0) G = 0;
+    if (G < gmin) G = gmin;
     polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
     h->smem_bytes = h->lay.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {

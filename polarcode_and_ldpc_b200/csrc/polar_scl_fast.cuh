@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
     double* cm = (double*)(wsm + Y.off_cm) + fr * NC;          // this frame's candidate keys
     double* newpm = (double*)(wsm + Y.off_newpm) + cbase;
     int* sel = (int*)(wsm + Y.off_sel) + cbase;
-    real* sl = (real*)(wsm + Y.off_llr);          // levels G+1 .. n-4, [k][col]
+    real* sl = (real*)(wsm + Y.off_llr);          // levels max(G,1)+1 .. n-4, [k][col]
     uint32_t* bw = (uint32_t*)(wsm + Y.off_bw);   // big left levels 1 .. nb, [w][col]
     uint32_t* uw = (uint32_t*)(wsm + Y.off_uw);   // final u words
     real* gl = P.scratch + (int64_t)(blockIdx.x * wpb + warp) * Y.scratch_per_warp;
@@ -186,52 +186,77 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             const uint32_t fz8 = (fw >> ((i0 + shift) & 31)) & 0xffu;
 
             // ---- levels above the cut: start .. n-3; the last one lands in registers ----
+            // Level 1 is never stored: level 2 recomputes its two level-1 operands from the
+            // channel LLRs on the fly (y[k] = llr[br(k)], y[k + N/2] = llr[br(k) + 1]), which
+            // removes the largest scratch array and its HBM round trips.
             real R3[E3];
 #pragma unroll
             for (int t = 0; t < E3; t++) R3[t] = (real)0;
             const int start = (blk == 0) ? 1 : n - (__ffs(i0) - 1);
-            for (int d = start; d <= n - 3; d++) {
+            const int dfirst = (n - 3 >= 2) ? 2 : 1;
+            const int bit1 = (i0 >> (n - 1)) & 1;
+            const uint32_t* b1src = bw + cbase + (ptrB & (LP - 1));      // left array of level 1 (nb >= 1)
+            auto lvl1 = [&](int m) -> real {
+                const int r = (int)(__brev((unsigned)m) >> (32 - n));
+                const real y0 = y[r], y1 = y[r + 1];
+                if (bit1) {
+                    const uint32_t ub = (nb >= 1) ? (b1src[(m >> 5) * LPF] >> (m & 31)) & 1u
+                                                  : (small >> ((32 - N + m) & 31)) & 1u;
+                    return pcl_fast<real>::g(y0, y1, ub);
+                }
+                return pcl_math<real>::f(y0, y1);
+            };
+            for (int d = (start > dfirst ? start : dfirst); d <= n - 3; d++) {
                 const int sz = N >> d;
                 const int bit = (i0 >> (n - d)) & 1;
+                const int hi = sz * LPF;                       // word distance of the partner element
                 const real* src = nullptr;                     // + sub-lane and borrowed column
-                if (d > 1) {
+                if (d > 2) {
                     const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
-                    src = ((d - 1 <= G) ? gl + (int64_t)LPF * (N - (N >> (d - 2)))
+                    src = ((d - 1 <= G) ? gl + (int64_t)LPF * ((N >> 1) - (N >> (d - 2)))
                                         : sl + LPF * ((N >> G) - (N >> (d - 2)))) + kk * LPF + cbase + q;
                 }
                 const uint32_t* bsrc = nullptr;
                 if (bit && d <= nb)
                     bsrc = bw + LPF * ((N >> 5) - (N >> (d + 4))) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
+                const uint32_t smf = small >> ((32 - 2 * sz) & 31);        // small-field partial sums of level d
                 if (d < n - 3) {
-                    real* dst = ((d <= G) ? gl + (int64_t)LPF * (N - (N >> (d - 1)))
+                    real* dst = ((d <= G) ? gl + (int64_t)LPF * ((N >> 1) - (N >> (d - 1)))
                                           : sl + LPF * ((N >> G) - (N >> (d - 1)))) + kk * LPF + col;
                     // element k = kk + S t sits at word offset 32 t of the [k][col] array
-                    const int hi = sz * LPF;
                     if (act) {
-                        if (d == 1) {
+                        if (d == 2) {
+#pragma unroll 2
                             for (int k = kk; k < sz; k += S) {
-                                const int r = (int)(__brev((unsigned)k) >> (32 - n));
-                                const real a = y[r], b = y[r + 1];
-                                uint32_t ub = 0;
-                                if (bit) ub = (d <= nb) ? (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u
-                                                        : (small >> (32 - 2 * sz + k)) & 1u;
-                                dst[(k - kk) * LPF] = bit ? pcl_fast<real>::g(a, b, ub) : pcl_math<real>::f(a, b);
-                            }
-                        } else if (!bit) {
-#pragma unroll 4
-                            for (int o = 0; o < hi; o += 32)
-                                if (o + kk * LPF < hi) dst[o] = pcl_math<real>::f(src[o], src[o + hi]);
-                        } else if (d <= nb) {
-                            for (int k = kk; k < sz; k += S) {
-                                const int o = (k - kk) * LPF;
-                                const uint32_t ub = (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u;
-                                dst[o] = pcl_fast<real>::g(src[o], src[o + hi], ub);
+                                const real a = lvl1(k), b = lvl1(k + sz);
+                                real v;
+                                if (bit) v = pcl_fast<real>::g(a, b, (d <= nb) ? (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u
+                                                                              : (smf >> k) & 1u);
+                                else v = pcl_math<real>::f(a, b);
+                                dst[(k - kk) * LPF] = v;
                             }
                         } else {
-                            const uint32_t sm = small >> (32 - 2 * sz);
-                            for (int k = kk; k < sz; k += S) {
-                                const int o = (k - kk) * LPF;
-                                dst[o] = pcl_fast<real>::g(src[o], src[o + hi], (sm >> k) & 1u);
+                            // batches of independent loads first: these arrays may live in L2 / HBM
+                            constexpr int UNR = 8;
+                            for (int o0 = 0; o0 < hi; o0 += 32 * UNR) {
+                                real a[UNR], b[UNR];
+#pragma unroll
+                                for (int e = 0; e < UNR; e++) {
+                                    const int o = o0 + 32 * e;
+                                    if (o < hi) { a[e] = src[o]; b[e] = src[o + hi]; }
+                                }
+#pragma unroll
+                                for (int e = 0; e < UNR; e++) {
+                                    const int o = o0 + 32 * e;
+                                    if (o < hi) {
+                                        const int k = kk + S * (o >> 5);
+                                        real v;
+                                        if (bit) v = pcl_fast<real>::g(a[e], b[e], (d <= nb) ? (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u
+                                                                                            : (smf >> k) & 1u);
+                                        else v = pcl_math<real>::f(a[e], b[e]);
+                                        dst[o] = v;
+                                    }
+                                }
                             }
                         }
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
@@ -247,6 +272,9 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                                 const int r = (int)(__brev((unsigned)k) >> (32 - n));
                                 a = y[r];
                                 b = y[r + 1];
+                            } else if (d == 2) {
+                                a = lvl1(k);
+                                b = lvl1(k + 8);
                             } else {
                                 a = src[32 * t];
                                 b = src[32 * t + 8 * LPF];
