@@ -23,8 +23,8 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.is_stale():
+    path = os.environ.get("PCL_LIB", _build.LIB)       # PCL_LIB: experiment builds of the same ABI
+    if path == _build.LIB and _build.is_stale():
         try:
             _build.build_native()
         except Exception as exc:  # stale-but-present is still usable on a box without nvcc

@@ -123,12 +123,42 @@ PCL_DEVICE int pcl_beats(double kj, double key, int jj, int c)
     return kj > key;
 }
 
+// rank += (kj > key) as one compare and one predicated add
+PCL_DEVICE void pcl_rank_acc(int& rank, double kj, double key)
+{
+#ifdef PCL_EMU
+    rank += kj > key;
+#else
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(rank) : "d"(kj), "d"(key));
+#endif
+}
+
+template <typename real>
+PCL_DEVICE void pcl_load_pair(const real* ptr, real& a, real& b);
+template <>
+PCL_DEVICE void pcl_load_pair<float>(const float* ptr, float& a, float& b)
+{
+    const float2 v = *reinterpret_cast<const float2*>(ptr);
+    a = v.x;
+    b = v.y;
+}
+template <>
+PCL_DEVICE void pcl_load_pair<double>(const double* ptr, double& a, double& b)
+{
+    const double2 v = *reinterpret_cast<const double2*>(ptr);
+    a = v.x;
+    b = v.y;
+}
+
 // LP = list slots per frame (power of two), S = lanes per path; a warp decodes
 // FPW = 32 / (LP * S) frames side by side.  All frames of a warp follow the same
 // schedule (frozen pattern, number of live paths), so every branch stays warp-uniform and
 // the per-leaf bookkeeping instructions are shared by FPW frames.
+#ifndef PCL_POLAR_MINB
+#define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for
+#endif
 template <int LP, int S, typename real>
-__global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P)
+__global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3) polar_scl_fast_kernel(PolarParams<real> P)
 {
     constexpr int PB = pcl_log2<LP>::v;
     constexpr int LPF = 32 / S;                  // columns = (frame, slot) pairs per warp
@@ -197,8 +227,9 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
             const int bit1 = (i0 >> (n - 1)) & 1;
             const uint32_t* b1src = bw + cbase + (ptrB & (LP - 1));      // left array of level 1 (nb >= 1)
             auto lvl1 = [&](int m) -> real {
-                const int r = (int)(__brev((unsigned)m) >> (32 - n));
-                const real y0 = y[r], y1 = y[r + 1];
+                const int r = (int)(__brev((unsigned)m) >> (32 - n));      // even: the pair is one aligned load
+                real y0, y1;
+                pcl_load_pair<real>(y + r, y0, y1);
                 if (bit1) {
                     const uint32_t ub = (nb >= 1) ? (b1src[(m >> 5) * LPF] >> (m & 31)) & 1u
                                                   : (small >> ((32 - N + m) & 31)) & 1u;
@@ -236,26 +267,26 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                                 dst[(k - kk) * LPF] = v;
                             }
                         } else {
-                            // batches of independent loads first: these arrays may live in L2 / HBM
-                            constexpr int UNR = 8;
+                            // batches of independent loads first: these arrays may live in L2 / HBM.
+                            // sz >= 16, so sz / S is a multiple of UNR and no tail handling is needed;
+                            // the UNR elements of a batch take their partial-sum bits from one word.
+                            constexpr int UNR = (S >= 4) ? 4 : 8;
                             for (int o0 = 0; o0 < hi; o0 += 32 * UNR) {
                                 real a[UNR], b[UNR];
 #pragma unroll
                                 for (int e = 0; e < UNR; e++) {
-                                    const int o = o0 + 32 * e;
-                                    if (o < hi) { a[e] = src[o]; b[e] = src[o + hi]; }
+                                    a[e] = src[o0 + 32 * e];
+                                    b[e] = src[o0 + 32 * e + hi];
                                 }
+                                if (bit) {
+                                    const int k0 = kk + S * (o0 >> 5);          // k of element e: k0 + S e
+                                    const uint32_t wbits = (d <= nb) ? bsrc[(k0 >> 5) * LPF] >> (k0 & 31) : smf >> k0;
 #pragma unroll
-                                for (int e = 0; e < UNR; e++) {
-                                    const int o = o0 + 32 * e;
-                                    if (o < hi) {
-                                        const int k = kk + S * (o >> 5);
-                                        real v;
-                                        if (bit) v = pcl_fast<real>::g(a[e], b[e], (d <= nb) ? (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u
-                                                                                            : (smf >> k) & 1u);
-                                        else v = pcl_math<real>::f(a[e], b[e]);
-                                        dst[o] = v;
-                                    }
+                                    for (int e = 0; e < UNR; e++)
+                                        dst[o0 + 32 * e] = pcl_fast<real>::g(a[e], b[e], (wbits >> (S * e)) & 1u);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < UNR; e++) dst[o0 + 32 * e] = pcl_math<real>::f(a[e], b[e]);
                                 }
                             }
                         }
@@ -348,7 +379,10 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                         int rank = 0;
                         if (seg < NSEG) {
 #pragma unroll
-                            for (int e = 0; e < CH; e++) rank += pcl_beats<EXACT>(cm[seg * CH + e], key, seg * CH + e, c);
+                            for (int e = 0; e < CH; e++) {
+                                if (EXACT) rank += pcl_beats<EXACT>(cm[seg * CH + e], key, seg * CH + e, c);
+                                else pcl_rank_acc(rank, cm[seg * CH + e], key);
+                            }
                         }
 #pragma unroll
                         for (int o = 1; o < NSEG; o <<= 1) rank += __shfl_xor_sync(PCL_FULL_MASK, rank, 2 * LPF * o);
@@ -363,11 +397,16 @@ __global__ void __launch_bounds__(128) polar_scl_fast_kernel(PolarParams<real> P
                         cm[LP + p] = kb;
                         __syncwarp();
                         int ra = 0, rb = 0;
-#pragma unroll 8
+#pragma unroll 16
                         for (int jj = 0; jj < NC; jj++) {
                             const double kj = cm[jj];
-                            ra += pcl_beats<EXACT>(kj, ka, jj, p);
-                            rb += pcl_beats<EXACT>(kj, kb, jj, LP + p);
+                            if (EXACT) {
+                                ra += pcl_beats<EXACT>(kj, ka, jj, p);
+                                rb += pcl_beats<EXACT>(kj, kb, jj, LP + p);
+                            } else {
+                                pcl_rank_acc(ra, kj, ka);
+                                pcl_rank_acc(rb, kj, kb);
+                            }
                         }
                         if (ra < ns) { sel[ra] = p; newpm[ra] = mca; }
                         if (rb < ns) { sel[rb] = LP + p; newpm[rb] = mcb; }
