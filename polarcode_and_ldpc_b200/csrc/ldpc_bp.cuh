@@ -232,7 +232,10 @@ PCL_DEVICE real vn_sum_np(const real* msg, const uint16_t* ed, int d)
     return res;
 }
 
-template <typename real, int MODE, int DMAX>
+// REG != 0: every check has degree DMAX and every variable degree 3 (the regular (3, DMAX)
+// Gallager codes of the benchmarks): degrees and edge offsets become compile-time constants,
+// no pointer-table loads and no per-edge degree predicates.
+template <typename real, int MODE, int DMAX, int REG>
 __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
 {
     const LdpcLayout& Y = P.lay;
@@ -261,8 +264,8 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
         for (int it = 0; it < Y.max_iter; it++) {
             // 1. check nodes (:152-168)
             for (int c = lane; c < m; c += 32) {
-                const int e0 = P.cptr[c];
-                const int d = P.cptr[c + 1] - e0;
+                const int e0 = REG ? c * DMAX : P.cptr[c];
+                const int d = REG ? DMAX : P.cptr[c + 1] - e0;
                 if (MODE == 1) {
                     cn_ms<real>(msg + e0, d, P.norm);
                 } else {
@@ -276,8 +279,8 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
                 const int v = vb + lane;
                 bool bit = false;
                 if (v < n) {
-                    const int j0 = P.vptr[v];
-                    const int d = P.vptr[v + 1] - j0;
+                    const int j0 = REG ? v * 3 : P.vptr[v];
+                    const int d = REG ? 3 : P.vptr[v + 1] - j0;
                     const uint16_t* ed = P.vperm + j0;
                     real total;
                     if (d == 3) {
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
             if (Y.early_stop) {
                 bool bad = false;
                 for (int c = lane; c < m; c += 32) {
-                    const int e0 = P.cptr[c], e1 = P.cptr[c + 1];
+                    const int e0 = REG ? c * DMAX : P.cptr[c], e1 = REG ? e0 + DMAX : P.cptr[c + 1];
                     unsigned par = 0;
                     for (int e = e0; e < e1; e++) {
                         const int v = P.col[e];

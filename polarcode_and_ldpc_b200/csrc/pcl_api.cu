@@ -92,7 +92,7 @@ static inline int bit_reverse_i(int v, int nbits)
 }
 
 // =============================================================== polar =========
-#define PCL_NSTAGE 2
+#define PCL_NSTAGE 3
 
 struct pcl_polar {
     int N, n, K, L, LP, dtype;
@@ -100,18 +100,18 @@ struct pcl_polar {
     PolarLayout lay;
     uint32_t* d_frozen_words = nullptr;
     uint16_t* d_info_pos = nullptr;
-    void* d_scratch[PCL_NSTAGE] = {nullptr, nullptr};
+    void* d_scratch[PCL_NSTAGE] = {};
     size_t scratch_bytes = 0;
     int wpb, grid_max, smem_bytes;
     int last_grid = 0;
     int fast = 0;               // register-resident tree bottom (polar_scl_fast.cuh)
     int S = 1, fpw = 1;         // fast kernel: lanes per path, frames per warp
     // host-buffer pipeline
-    void* d_llr[PCL_NSTAGE] = {nullptr, nullptr};
-    uint8_t* d_bits[PCL_NSTAGE] = {nullptr, nullptr};
+    void* d_llr[PCL_NSTAGE] = {};
+    uint8_t* d_bits[PCL_NSTAGE] = {};
     int64_t chunk = 0;
 #ifndef PCL_EMU
-    cudaStream_t st[PCL_NSTAGE] = {nullptr, nullptr};
+    cudaStream_t st[PCL_NSTAGE] = {};
 #endif
 };
 
@@ -381,7 +381,7 @@ extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64
     return fail(PCL_ECUDA, "no CUDA device");
 #else
     const size_t rsz = real_size(h->dtype);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 32768)));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 8192)));
     if (h->chunk < chunk) {
         for (int s = 0; s < PCL_NSTAGE; s++) {
             cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]);
@@ -417,56 +417,56 @@ extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64
 // ================================================================ LDPC =========
 struct pcl_ldpc {
     int m, n, E, mode, max_iter, early_stop, dtype, dmax;
+    int regular6 = 0;           // every check degree 6, every variable degree 3
     double norm;
     LdpcLayout lay;
     int32_t* d_cptr = nullptr;
     uint16_t* d_col = nullptr;
     int32_t* d_vptr = nullptr;
     uint16_t* d_vperm = nullptr;
-    unsigned long long* d_next[PCL_NSTAGE] = {nullptr, nullptr};
+    unsigned long long* d_next[PCL_NSTAGE] = {};
     int wpb, grid_max, smem_bytes, last_grid = 0;
-    void* d_llr[PCL_NSTAGE] = {nullptr, nullptr};
-    uint8_t* d_bits[PCL_NSTAGE] = {nullptr, nullptr};
-    int32_t* d_iters[PCL_NSTAGE] = {nullptr, nullptr};
+    void* d_llr[PCL_NSTAGE] = {};
+    uint8_t* d_bits[PCL_NSTAGE] = {};
+    int32_t* d_iters[PCL_NSTAGE] = {};
     int64_t chunk = 0;
 #ifndef PCL_EMU
-    cudaStream_t st[PCL_NSTAGE] = {nullptr, nullptr};
+    cudaStream_t st[PCL_NSTAGE] = {};
 #endif
 };
 
-template <typename real, int MODE, int DMAX>
-static int ldpc_launch_t(pcl_ldpc* h, const LdpcParams<real>& P, int grid, void* stream)
+template <typename real, typename Fn>
+static int ldpc_with_kernel(pcl_ldpc* h, Fn&& fn)
 {
-    (void)stream;
-    auto kern = ldpc_decode_kernel<real, MODE, DMAX>;
-    PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
-    return PCL_OK;
+    if (h->mode == PCL_LDPC_MS) {
+        if (h->regular6) return fn(ldpc_decode_kernel<real, 1, 6, 1>);
+        return fn(ldpc_decode_kernel<real, 1, 8, 0>);
+    }
+    if (h->regular6) return fn(ldpc_decode_kernel<real, 0, 6, 1>);
+    if (h->dmax <= 8) return fn(ldpc_decode_kernel<real, 0, 8, 0>);
+    if (h->dmax <= 16) return fn(ldpc_decode_kernel<real, 0, 16, 0>);
+    return fn(ldpc_decode_kernel<real, 0, 32, 0>);
 }
 
 template <typename real>
 static int ldpc_launch(pcl_ldpc* h, const LdpcParams<real>& P, int grid, void* stream)
 {
-    if (h->mode == PCL_LDPC_MS) return ldpc_launch_t<real, 1, 8>(h, P, grid, stream);
-    if (h->dmax <= 8) return ldpc_launch_t<real, 0, 8>(h, P, grid, stream);
-    if (h->dmax <= 16) return ldpc_launch_t<real, 0, 16>(h, P, grid, stream);
-    return ldpc_launch_t<real, 0, 32>(h, P, grid, stream);
+    (void)stream;
+    return ldpc_with_kernel<real>(h, [&](auto kern) -> int {
+        PCL_LAUNCH(kern, grid, h->wpb * 32, h->smem_bytes, stream, P);
+        return PCL_OK;
+    });
 }
 
 #ifndef PCL_EMU
-template <typename real, int MODE, int DMAX>
-static int ldpc_occ_t(int threads, int smem, int* bps)
-{
-    CUDA_TRY(cudaFuncSetAttribute(ldpc_decode_kernel<real, MODE, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, ldpc_decode_kernel<real, MODE, DMAX>, threads, smem));
-    return PCL_OK;
-}
 template <typename real>
 static int ldpc_occ(pcl_ldpc* h, int threads, int smem, int* bps)
 {
-    if (h->mode == PCL_LDPC_MS) return ldpc_occ_t<real, 1, 8>(threads, smem, bps);
-    if (h->dmax <= 8) return ldpc_occ_t<real, 0, 8>(threads, smem, bps);
-    if (h->dmax <= 16) return ldpc_occ_t<real, 0, 16>(threads, smem, bps);
-    return ldpc_occ_t<real, 0, 32>(threads, smem, bps);
+    return ldpc_with_kernel<real>(h, [&](auto kern) -> int {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem));
+        return PCL_OK;
+    });
 }
 #endif
 
@@ -511,6 +511,12 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     pcl_ldpc* h = new pcl_ldpc();
     h->m = m; h->n = n; h->E = E; h->mode = mode; h->max_iter = max_iter; h->early_stop = early_stop ? 1 : 0;
     h->dtype = dtype; h->dmax = dmax; h->norm = normalization;
+    {
+        bool reg = env_int("PCL_LDPC_GENERIC", 0) == 0;
+        for (int c = 0; c < m && reg; c++) reg = (cptr[c + 1] - cptr[c]) == 6;
+        for (int v = 0; v < n && reg; v++) reg = vdeg[v] == 3;
+        h->regular6 = reg ? 1 : 0;
+    }
     const int rsz = (int)real_size(dtype);
     LdpcLayout& Y = h->lay;
     Y.m = m; Y.n = n; Y.E = E; Y.max_iter = max_iter; Y.early_stop = h->early_stop;
@@ -524,8 +530,17 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) { delete h; return rc; }
-    h->wpb = env_int("PCL_LDPC_WPB", 4);
-    if (h->wpb < 1 || h->wpb > 8) h->wpb = 4;
+    // warps per block: the split of the SM's shared memory that keeps most frames resident
+    h->wpb = env_int("PCL_LDPC_WPB", 0);
+    if (h->wpb < 1 || h->wpb > 8) {
+        int best_w = 1, best_res = 0;
+        for (int w = 1; w <= 4; w++) {
+            if (Y.warp_bytes * w > di.smem_per_block) break;
+            int res = (di.smem_per_sm / (Y.warp_bytes * w + 1024)) * w;
+            if (res >= best_res) { best_res = res; best_w = w; }
+        }
+        h->wpb = best_w;
+    }
     while (h->wpb > 1 && Y.warp_bytes * h->wpb > di.smem_per_block) h->wpb >>= 1;
     h->smem_bytes = Y.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
@@ -626,7 +641,7 @@ extern "C" int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t
     return fail(PCL_ECUDA, "no CUDA device");
 #else
     const size_t rsz = real_size(h->dtype);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 32768)));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 8192)));
     if (h->chunk < chunk) {
         for (int s = 0; s < PCL_NSTAGE; s++) {
             cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
