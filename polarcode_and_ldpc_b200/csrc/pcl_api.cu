@@ -127,7 +127,7 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
     Y.nb = Y.n > 5 ? Y.n - 5 : 0;
     Y.uw_slots = crc ? cols : fpw;
     int off = 0;
-    Y.off_cm = off;     off += 2 * cols * 8;
+    Y.off_cm = off;     off += (2 * cols + 2 * fpw) * 8;       // per frame: 2 LP keys + 2 pad (bank spread)
     Y.off_newpm = off;  off += cols * 8;
     // generic kernel keeps levels G+1 .. n-1 in shared memory, the fast one G+1 .. n-4
     // (the fast kernel never stores level 1, so its G is at least 1)

@@ -134,6 +134,22 @@ PCL_DEVICE void pcl_rank_acc(int& rank, double kj, double key)
 }
 
 template <typename real>
+PCL_DEVICE void pcl_load_quad(const real* ptr, real* v);
+template <>
+PCL_DEVICE void pcl_load_quad<float>(const float* ptr, float* v)
+{
+    const float4 q = *reinterpret_cast<const float4*>(ptr);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <>
+PCL_DEVICE void pcl_load_quad<double>(const double* ptr, double* v)
+{
+    const double2 q0 = *reinterpret_cast<const double2*>(ptr);
+    const double2 q1 = *reinterpret_cast<const double2*>(ptr + 2);
+    v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+}
+
+template <typename real>
 PCL_DEVICE void pcl_load_pair(const real* ptr, real& a, real& b);
 template <>
 PCL_DEVICE void pcl_load_pair<float>(const float* ptr, float& a, float& b)
@@ -188,7 +204,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
     const int NB = N >> 3;
 
     unsigned char* wsm = pcl_dyn_smem() + (size_t)warp * Y.warp_bytes;
-    double* cm = (double*)(wsm + Y.off_cm) + fr * NC;          // this frame's candidate keys
+    double* cm = (double*)(wsm + Y.off_cm) + fr * (NC + 2);    // this frame's candidate keys (padded: banks)
     double* newpm = (double*)(wsm + Y.off_newpm) + cbase;
     int* sel = (int*)(wsm + Y.off_sel) + cbase;
     real* sl = (real*)(wsm + Y.off_llr);          // levels max(G,1)+1 .. n-4, [k][col]
@@ -257,26 +273,56 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                     // element k = kk + S t sits at word offset 32 t of the [k][col] array
                     if (act) {
                         if (d == 2) {
-#pragma unroll 2
-                            for (int k = kk; k < sz; k += S) {
-                                const real a = lvl1(k), b = lvl1(k + sz);
+                            // Level-2 element k needs level-1 elements k and k + N/4, i.e. the channel
+                            // pairs at br(k) and br(k) + 2: ONE aligned 4-element load.  Walking t = br(k)
+                            // upwards makes those loads sequential in memory.
+                            real* dst2 = dst - kk * LPF;
+#pragma unroll 4
+                            for (int t = kk; t < sz; t += S) {
+                                const int k = (int)(__brev((unsigned)t) >> (34 - n));      // (n-2)-bit reversal
+                                real yv[4];
+                                pcl_load_quad<real>(y + 4 * t, yv);
+                                real a, b;
+                                if (bit1) {
+                                    uint32_t ua, ub;
+                                    if (nb >= 1) {
+                                        ua = (b1src[(k >> 5) * LPF] >> (k & 31)) & 1u;
+                                        ub = (b1src[((k + sz) >> 5) * LPF] >> ((k + sz) & 31)) & 1u;
+                                    } else {
+                                        ua = (small >> ((32 - N + k) & 31)) & 1u;
+                                        ub = (small >> ((32 - N + k + sz) & 31)) & 1u;
+                                    }
+                                    a = pcl_fast<real>::g(yv[0], yv[1], ua);
+                                    b = pcl_fast<real>::g(yv[2], yv[3], ub);
+                                } else {
+                                    a = pcl_math<real>::f(yv[0], yv[1]);
+                                    b = pcl_math<real>::f(yv[2], yv[3]);
+                                }
                                 real v;
                                 if (bit) v = pcl_fast<real>::g(a, b, (d <= nb) ? (bsrc[(k >> 5) * LPF] >> (k & 31)) & 1u
                                                                               : (smf >> k) & 1u);
                                 else v = pcl_math<real>::f(a, b);
-                                dst[(k - kk) * LPF] = v;
+                                dst2[k * LPF] = v;
                             }
                         } else {
-                            // batches of independent loads first: these arrays may live in L2 / HBM.
-                            // sz >= 16, so sz / S is a multiple of UNR and no tail handling is needed;
-                            // the UNR elements of a batch take their partial-sum bits from one word.
-                            constexpr int UNR = (S >= 4) ? 4 : 8;
-                            for (int o0 = 0; o0 < hi; o0 += 32 * UNR) {
-                                real a[UNR], b[UNR];
+                            // Software-pipelined batches of independent loads: these arrays may live in
+                            // L2 / HBM.  sz >= 16, so sz / S is a multiple of UNR (no tail); the UNR
+                            // elements of a batch take their partial-sum bits from one word.
+                            constexpr int UNR = 4;
+                            real a[UNR], b[UNR], a2[UNR], b2[UNR];
 #pragma unroll
-                                for (int e = 0; e < UNR; e++) {
-                                    a[e] = src[o0 + 32 * e];
-                                    b[e] = src[o0 + 32 * e + hi];
+                            for (int e = 0; e < UNR; e++) {
+                                a[e] = src[32 * e];
+                                b[e] = src[32 * e + hi];
+                            }
+                            for (int o0 = 0; o0 < hi; o0 += 32 * UNR) {
+                                const int o1 = o0 + 32 * UNR;
+                                if (o1 < hi) {
+#pragma unroll
+                                    for (int e = 0; e < UNR; e++) {
+                                        a2[e] = src[o1 + 32 * e];
+                                        b2[e] = src[o1 + 32 * e + hi];
+                                    }
                                 }
                                 if (bit) {
                                     const int k0 = kk + S * (o0 >> 5);          // k of element e: k0 + S e
@@ -288,6 +334,8 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
 #pragma unroll
                                     for (int e = 0; e < UNR; e++) dst[o0 + 32 * e] = pcl_math<real>::f(a[e], b[e]);
                                 }
+#pragma unroll
+                                for (int e = 0; e < UNR; e++) { a[e] = a2[e]; b[e] = b2[e]; }
                             }
                         }
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
