@@ -93,11 +93,11 @@ PCL_DEVICE void cn_bp_exact(double* msg, int d)
 
 // ---- check node, fp32 production rule (t and w = 1 - |t| side by side) ---------
 // MUFU budget per edge: ex2 + rcp on the way in, rcp + lg2 on the way out.
-//   u = exp(-|x|) (split-constant range reduction, rel. err ~1e-7)
+//   u = exp(-|x|) = 2^(-|x| log2 e) (rel. err ~ |x| * 6e-8: enters the outgoing LLR additively)
 //   w = 1 - tanh(|x|/2) = 2u / (1 + u)   keeps full RELATIVE precision near |t| -> 1,
 //   t = (1 - u) / (1 + u)                keeps full ABSOLUTE precision near t -> 0.
 // Leave-one-out: p_i = prod t_j, q_i = 1 - prod (1 - w_j) (sums of positive terms, no
-// cancellation).  Output 2 atanh(p): q < 1/4 -> ln((2-q)/q); |p| < 1/4 -> odd series;
+// cancellation).  Output 2 atanh(p): q < 1/4 -> ln((2-q)/q); |p| < 1/8 -> odd series;
 // otherwise ln((1+|p|)/(1-|p|)).  Both clips of the reference (+-0.999999 on t and on the
 // product, decoder.py:82,88) become w >= 1e-6 and q >= 1e-6.
 PCL_DEVICE float pcl_ex2(float x)
@@ -134,25 +134,25 @@ PCL_DEVICE float pcl_rcp(float x)
 template <int DMAX>
 PCL_DEVICE void cn_bp_f32(float* msg, int d)
 {
+    // magnitudes and signs travel separately: products of non-negative numbers only, the
+    // leave-one-out sign is an XOR of sign bits
     float t[DMAX], w[DMAX];
+    uint32_t sg[DMAX];
+    uint32_t sall = 0;
 #pragma unroll
     for (int j = 0; j < DMAX; j++) {
         if (j < d) {
             const float x = msg[j];
-            const float a = fabsf(x);
-            // -a * log2(e) as hi + lo
-            const float th = a * -1.4426950216293335f;
-            const float tl = fmaf(a, -1.4426950216293335f, -th) + a * -1.9259629911266175e-8f;
-            float u = pcl_ex2(th);
-            u = fmaf(u, tl * 0.6931471805599453f, u);
+            const float u = pcl_ex2(fabsf(x) * -1.4426950408889634f);   // exp(-|x|), rel. err ~ |x| * 6e-8
             const float r = pcl_rcp(1.0f + u);
-            const float wv = fmaxf(2.0f * u * r, 1e-6f);       // 1 - |t|, clipped
-            float tv = fminf((1.0f - u) * r, 0.999999f);       // |t|, clipped
-            t[j] = (x < 0.0f) ? -tv : tv;
-            w[j] = wv;
+            w[j] = fmaxf((u + u) * r, 1e-6f);                           // 1 - |t|, clipped
+            t[j] = fminf((1.0f - u) * r, 0.999999f);                    // |t|, clipped
+            sg[j] = __float_as_uint(x) & 0x80000000u;
+            sall ^= sg[j];
         } else {
             t[j] = 1.0f;
             w[j] = 0.0f;
+            sg[j] = 0u;
         }
     }
     // suffix products, then a running prefix
@@ -168,19 +168,17 @@ PCL_DEVICE void cn_bp_f32(float* msg, int d)
 #pragma unroll
     for (int i = 0; i < DMAX; i++) {
         if (i < d) {
-            const float pr = pt * st[i + 1];
-            const float ap = fabsf(pr);
-            float q = fmaf(-pq, sq[i + 1], pq + sq[i + 1]);
+            const float ap = pt * st[i + 1];                    // |p_i|
+            float q = fmaf(-pq, sq[i + 1], pq + sq[i + 1]);     // 1 - |p_i| from the w side
             q = fmaxf(q, 1e-6f);                                // |p| <= 0.999999
             const bool near1 = q < 0.25f;
             const float num = near1 ? 2.0f - q : 1.0f + ap;
             const float den = near1 ? q : 1.0f - ap;
             float mag = 0.6931471805599453f * pcl_lg2(num * pcl_rcp(den));
             const float p2 = ap * ap;
-            const float ser = 2.0f * ap * fmaf(p2, fmaf(p2, fmaf(p2, fmaf(p2, 0.11111111f, 0.14285715f), 0.2f),
-                                                        0.33333334f), 1.0f);
-            if (!near1 && ap < 0.25f) mag = ser;
-            msg[i] = (pr < 0.0f) ? -mag : mag;
+            const float ser = (ap + ap) * fmaf(p2, fmaf(p2, fmaf(p2, 0.14285715f, 0.2f), 0.33333334f), 1.0f);
+            if (ap < 0.125f) mag = ser;                         // q >= 0.875 there, never near1
+            msg[i] = __uint_as_float(__float_as_uint(mag) | (sall ^ sg[i]));
         }
         pt = pt * t[i];
         pq = fmaf(-pq, w[i], pq + w[i]);

@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                             // Software-pipelined batches of independent loads: these arrays may live in
                             // L2 / HBM.  sz >= 16, so sz / S is a multiple of UNR (no tail); the UNR
                             // elements of a batch take their partial-sum bits from one word.
-                            constexpr int UNR = 4;
+#ifndef PCL_POLAR_UNR
+#define PCL_POLAR_UNR 8
+#endif
+                            constexpr int UNR = (S >= 4 && PCL_POLAR_UNR > 4) ? 4 : PCL_POLAR_UNR;
                             real a[UNR], b[UNR], a2[UNR], b2[UNR];
 #pragma unroll
                             for (int e = 0; e < UNR; e++) {
