@@ -377,54 +377,13 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
             for (int t = 0; t < E2; t++) R2[t] = (real)0;
 #pragma unroll
             for (int t = 0; t < E1; t++) R1[t] = (real)0;
-            // ---- all-frozen block (S == 1): the 8 leaf LLRs follow from the block root with all
-            // partial sums zero, so the whole butterfly is evaluated at once; the metric still
-            // takes the 8 leaf terms in decode order (same additions as the leaf-by-leaf path).
-            int jfirst = 0;
-            if (S == 1 && LP > 1 && fz8 == 0xffu && E3 == 8) {
-                real T[8], U[8], X[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    T[k] = pcl_math<real>::f(R3[k], R3[k + 4]);
-                    T[k + 4] = R3[k + 4] + R3[k];
-                }
-#pragma unroll
-                for (int hh = 0; hh < 8; hh += 4) {
-#pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        U[hh + k] = pcl_math<real>::f(T[hh + k], T[hh + k + 2]);
-                        U[hh + k + 2] = T[hh + k + 2] + T[hh + k];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k += 2) {
-                    X[k] = pcl_math<real>::f(U[k], U[k + 1]);
-                    X[k + 1] = U[k + 1] + U[k];
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const real xk = act ? X[k] : (real)0;
-                    const real axk = fabs(xk);
-                    const real pen = pcl_fast<real>::softplus_neg_abs(axk) + (!(xk >= (real)0) ? axk : (real)0);
-                    if (act) pm -= (double)pen;
-                    if (P.dbg_leaf != nullptr && valid) {
-                        P.dbg_leaf[(f * N + i0 + k) * LP + p] = xk;
-                        P.dbg_parent[(f * N + i0 + k) * LP + p] = (uint8_t)p;
-                    }
-                }
-                small &= ~(0x7fu << 24);            // partial sums of sizes 1, 2, 4: all zero
-                jfirst = 7;                         // fall into the j == 7 tail to close the block
-            }
 #pragma unroll 1
-            for (int j = jfirst; j < 8; j++) {
+            for (int j = 0; j < 8; j++) {
                 const int i = i0 + j;
                 const bool frozen = (fz8 >> j) & 1u;
-                const bool shortcut = (jfirst == 7);
                 // heights to recompute: j == 0 -> 2,1,0; else ctz(j) .. 0; f or g per bit of j
-                real x = (real)0;
-                if (shortcut) {
-                    // leaf 7 of an all-frozen block: LLR, metric and debug output already done
-                } else if (j & 1) {
+                real x;
+                if (j & 1) {
                     pcl_block_stage<LPF, S, 1, true, real>(&x, R1, small, kk, lane);
                 } else {
                     if ((j & 2) == 0) {
@@ -438,14 +397,13 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                 }
                 if (S > 1) x = pcl_shfl_real<real>(x, col);        // lane `col` is sub-lane 0 of the path
                 if (!act) x = (real)0;
-                uint32_t u = 0;
-                int parent = p;
-                bool forked = false;
-                if (!shortcut) {
 
                 // ---- leaf decision (polar_scl.cuh for the rules) -------------------------
                 const real ax = fabs(x);
                 const bool hard = !(x >= (real)0);
+                uint32_t u = 0;
+                int parent = p;
+                bool forked = false;
                 if (LP == 1) {
                     u = frozen ? 0u : (hard ? 1u : 0u);
                     if (P.want_pm) {
@@ -515,11 +473,6 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                     if (!act) pm = NEG_INF;
                     nact = ns;
                 }
-                if (P.dbg_leaf != nullptr && kk == 0 && valid && !forked) {
-                    P.dbg_leaf[(f * N + i) * LP + p] = x;
-                    P.dbg_parent[(f * N + i) * LP + p] = (uint8_t)p;
-                }
-                }   // !shortcut
                 if (forked) {
                     // a survivor takes over its parent's pointer words and live registers
                     const int srcl = (lane & ~(LP - 1)) | parent;
@@ -540,7 +493,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                     }
                     __syncwarp();
                 }
-                if (P.dbg_leaf != nullptr && kk == 0 && valid && forked) {
+                if (P.dbg_leaf != nullptr && kk == 0 && valid) {
                     P.dbg_leaf[(f * N + i) * LP + p] = x;
                     P.dbg_parent[(f * N + i) * LP + p] = (uint8_t)parent;
                 }
