@@ -80,7 +80,9 @@ def main():
                 "fp64_frames_differing": int(((b64 != rb).any(axis=1) | (i64 != ri)).sum()),
                 "fp32_frames_differing": int((~same32).sum()),
                 "fp64_total_llr_max_rel_err": rel_err(t64, rt, floor),
-                "fp32_total_llr_max_rel_err_same_frames": rel_err(t32[same32], rt[same32], floor)})
+                "fp32_total_llr_max_rel_err_same_frames": rel_err(t32[same32], rt[same32], floor),
+                "fp32_total_llr_rel_err_p9999": float(np.quantile(
+                    np.abs(t32[same32] - rt[same32]) / np.maximum(np.abs(rt[same32]), floor), 0.9999))})
             print(rep["cases"][-1], flush=True)
     tot = sum(c["frames"] for c in rep["cases"])
     rep["total_frames"] = tot
