@@ -61,6 +61,18 @@ def info_bits(w):
     return w["K"] if w["kind"] == "polar" else w["k"]
 
 
+def measured_traffic(name, frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the workload's kernel from the committed
+    `ncu --set full` capture (profiles/latest.json: bytes per frame), scaled to one launch."""
+    p = os.path.join(ROOT, "profiles", "latest.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(name)
+    if not d:
+        return None, None
+    return d["dram_bytes_per_frame"] * frames, d["source"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -230,14 +242,16 @@ def run_gpu_workload(name, args, torch, dist, rank, world, device, with_e2e=True
     hbm_peak, peak_src, sm_max = peaks()
     achieved = alg * F / (ms_kernel * 1e-3) / 1e9
     smem_peak = 148 * 128 * sm_max * 1e6 / 1e9
+    traffic, traffic_src = measured_traffic(name, F)
     res = {
         "workload": name, "desc": w["desc"], "frames_per_gpu_per_step": F, "gbps": gbps, "ms_per_step": ms_step,
         "ms_kernel": ms_kernel, "frames_per_s": world * F / (ms_step * 1e-3), "e2e": e2e,
         "fer": c[1] / max(c[2], 1), "ber": c[0] / max(c[3], 1), "frames_counted": c[2],
         "launch": info, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_frame": alg, "kernel": "polar_scl_kernel" if w["kind"] == "polar" else "ldpc_decode_kernel",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "algorithmic_bytes_per_frame": alg,
+                     "kernel": info.get("kernel", "ldpc_decode_kernel"),
                      "onchip": {"bound": "smem", "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
                                 "note": "148 SMs x 128 B/clk x max SM clock; the path is SMEM/issue bound, HBM sees only "
                                         f"{(4 * (w.get('N') or w.get('n')) + (w.get('K') or w.get('n')))} B/frame"}},
