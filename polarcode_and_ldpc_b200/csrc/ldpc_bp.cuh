@@ -42,6 +42,7 @@ struct LdpcParams {
     const uint16_t* col;        // [E] variable of edge e
     const int32_t* vptr;        // [n+1]
     const uint16_t* vperm;      // [E] edge ids, variable-major
+    const unsigned long long* vpack;  // REG: per variable, its 3 edge ids packed 16 bits each
     unsigned long long* next;   // dynamic frame counter
     int64_t F;
     real norm;                  // Min-Sum normalisation
@@ -273,33 +274,48 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
             }
             __syncwarp();
             // 2. variable nodes (:173-188) + 3. hard decision (:191)
+            // (hard decisions are only materialised when something reads them: the syndrome test
+            // or the output after the last iteration)
+            const bool want_hard = Y.early_stop || it == Y.max_iter - 1;
             for (int vb = 0; vb < n; vb += 32) {
                 const int v = vb + lane;
                 bool bit = false;
                 if (v < n) {
-                    const int j0 = REG ? v * 3 : P.vptr[v];
-                    const int d = REG ? 3 : P.vptr[v + 1] - j0;
-                    const uint16_t* ed = P.vperm + j0;
                     real total;
-                    if (d == 3) {
-                        const int ea = ed[0], eb = ed[1], ec = ed[2];
+                    if (REG) {
+                        const unsigned long long pk = P.vpack[v];
+                        const int ea = (int)(pk & 0xffffu), eb = (int)((pk >> 16) & 0xffffu), ec = (int)((pk >> 32) & 0xffffu);
                         const real ma = msg[ea], mb = msg[eb], mc = msg[ec];
                         total = sllr[v] + ((((real)0 + ma) + mb) + mc);
                         msg[ea] = total - ma;
                         msg[eb] = total - mb;
                         msg[ec] = total - mc;
                     } else {
-                        total = sllr[v] + vn_sum_np<real>(msg, ed, d);
-                        for (int j = 0; j < d; j++) {
-                            const int e = ed[j];
-                            msg[e] = total - msg[e];
+                        const int j0 = P.vptr[v];
+                        const int d = P.vptr[v + 1] - j0;
+                        const uint16_t* ed = P.vperm + j0;
+                        if (d == 3) {
+                            const int ea = ed[0], eb = ed[1], ec = ed[2];
+                            const real ma = msg[ea], mb = msg[eb], mc = msg[ec];
+                            total = sllr[v] + ((((real)0 + ma) + mb) + mc);
+                            msg[ea] = total - ma;
+                            msg[eb] = total - mb;
+                            msg[ec] = total - mc;
+                        } else {
+                            total = sllr[v] + vn_sum_np<real>(msg, ed, d);
+                            for (int j = 0; j < d; j++) {
+                                const int e = ed[j];
+                                msg[e] = total - msg[e];
+                            }
                         }
                     }
                     bit = (total <= (real)0);
                     if (P.total != nullptr) P.total[f * n + v] = total;
                 }
-                const unsigned bal = __ballot_sync(PCL_FULL_MASK, bit);
-                if (lane == 0) hard[vb >> 5] = bal;
+                if (want_hard) {
+                    const unsigned bal = __ballot_sync(PCL_FULL_MASK, bit);
+                    if (lane == 0) hard[vb >> 5] = bal;
+                }
             }
             __syncwarp();
             // 4. syndrome early stop (:194-198)

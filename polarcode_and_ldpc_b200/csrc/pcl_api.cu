@@ -424,6 +424,7 @@ struct pcl_ldpc {
     uint16_t* d_col = nullptr;
     int32_t* d_vptr = nullptr;
     uint16_t* d_vperm = nullptr;
+    unsigned long long* d_vpack = nullptr;
     unsigned long long* d_next[PCL_NSTAGE] = {};
     int wpb, grid_max, smem_bytes, last_grid = 0;
     void* d_llr[PCL_NSTAGE] = {};
@@ -566,6 +567,14 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     if (ok && E)
         ok = cudaMemcpy(h->d_col, col.data(), (size_t)E * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
              cudaMemcpy(h->d_vperm, vperm.data(), (size_t)E * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && h->regular6) {
+        std::vector<unsigned long long> vpack(n);
+        for (int v = 0; v < n; v++)
+            vpack[v] = (unsigned long long)vperm[vptr[v]] | ((unsigned long long)vperm[vptr[v] + 1] << 16) |
+                       ((unsigned long long)vperm[vptr[v] + 2] << 32);
+        ok = cudaMalloc((void**)&h->d_vpack, (size_t)n * 8) == cudaSuccess &&
+             cudaMemcpy(h->d_vpack, vpack.data(), (size_t)n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) { pcl_ldpc_destroy(h); return fail(PCL_ECUDA, "device table setup failed"); }
     *out = h;
     return PCL_OK;
@@ -574,7 +583,7 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
 extern "C" void pcl_ldpc_destroy(pcl_ldpc_t* h)
 {
     if (!h) return;
-    cudaFree(h->d_cptr); cudaFree(h->d_col); cudaFree(h->d_vptr); cudaFree(h->d_vperm);
+    cudaFree(h->d_cptr); cudaFree(h->d_col); cudaFree(h->d_vptr); cudaFree(h->d_vperm); cudaFree(h->d_vpack);
     for (int s = 0; s < PCL_NSTAGE; s++) {
         cudaFree(h->d_next[s]); cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
 #ifndef PCL_EMU
@@ -605,7 +614,7 @@ static int ldpc_decode_impl(pcl_ldpc* h, const void* llr_dev, int64_t F, uint8_t
     P.bits = bits_dev;
     P.iters = iters_dev;
     P.total = (real*)total_dev;
-    P.cptr = h->d_cptr; P.col = h->d_col; P.vptr = h->d_vptr; P.vperm = h->d_vperm;
+    P.cptr = h->d_cptr; P.col = h->d_col; P.vptr = h->d_vptr; P.vperm = h->d_vperm; P.vpack = h->d_vpack;
     P.next = next;
     P.F = F;
     P.norm = (real)h->norm;
