@@ -359,3 +359,22 @@ def test_generic_kernel_fallback_matches(golden_dir):
         os.environ.pop("PCL_POLAR_GENERIC")
     assert P.SCLDecoder(1024, 512, 8, P.bhattacharyya_frozen_set(1024, 512, 2.0)).launch_info()["kernel"] == \
         "polar_scl_fast_kernel"
+
+
+@pytest.mark.parametrize("S", [1, 2, 4])
+def test_lanes_per_path_variants(S):
+    """PCL_POLAR_S selects how many lanes share a path (and hence how many frames share a warp);
+    every variant must give the oracle's bits, also for batches that leave a warp partly empty."""
+    os.environ["PCL_POLAR_S"] = str(S)
+    try:
+        for N, K, L, F in ((512, 256, 8, 1003), (1024, 700, 4, 517), (128, 64, 2, 999), (2048, 1024, 8, 130)):
+            frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+            _, llr = _polar_frames(N, K, frozen, F, 0.5, N + L + S)
+            ref = oracle.polar_scl(N, L, frozen, llr, nthreads=8)
+            for dt in DTYPES:
+                dec = P.SCLDecoder(N, K, list_size=L, frozen_bits=frozen, dtype=dt)
+                got = dec.decode_batch(llr)
+                bad = int((got != ref).any(axis=1).sum())
+                assert bad == 0 if dt == "float64" else bad <= 1, f"N={N} L={L} S={S} {dt}: {bad} frames differ"
+    finally:
+        os.environ.pop("PCL_POLAR_S")
