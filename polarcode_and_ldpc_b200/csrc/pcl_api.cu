@@ -135,20 +135,11 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
                         : ((G >= Y.n - 1) ? 0 : cols * ((N >> G) - 2));
     Y.off_llr = off;    off += align_up(llr_vals * rsz, 8);
     Y.off_sel = off;    off += cols * 4;
-    // fast kernel, N >= 256: the two largest left arrays (levels 1, 2: 3/4 of all words) go to the
-    // global scratch; the shared memory they free holds one more LLR level
-    Y.gbw = (fast && Y.nb >= 3 && env_int("PCL_POLAR_GBW", 2) > 0) ? 2 : 0;
-    const int bw_words_total = N >= 64 ? (N / 32 - 1) : 0;
-    const int bw_words_global = Y.gbw ? (N >> 6) + (N >> 7) : 0;
-    Y.off_bw = off;     off += cols * (bw_words_total - bw_words_global) * 4;
+    Y.off_bw = off;     off += cols * (N >= 64 ? (N / 32 - 1) : 0) * 4;
     Y.off_uw = off;     off += Y.uw_slots * Y.NW * 4;
     Y.warp_bytes = align_up(off, 16);
-    Y.scratch_llr_per_warp = fast ? (int64_t)cols * ((N >> 1) - (N >> G))     // levels 2 .. G
-                                  : (int64_t)cols * (N - (N >> G));           // levels 1 .. G
-    // + the global left arrays (32-bit words, counted in units of `real`, kept 16-byte aligned)
-    Y.scratch_llr_per_warp = (Y.scratch_llr_per_warp + 3) / 4 * 4;
-    Y.scratch_per_warp = Y.scratch_llr_per_warp + ((int64_t)cols * bw_words_global * 4 + rsz - 1) / rsz;
-    Y.scratch_per_warp = (Y.scratch_per_warp + 3) / 4 * 4;
+    Y.scratch_per_warp = fast ? (int64_t)cols * ((N >> 1) - (N >> G))     // levels 2 .. G
+                              : (int64_t)cols * (N - (N >> G));           // levels 1 .. G
 }
 
 // Kernel variants.  Generic: one frame per warp, every level in shared memory.  Fast: S lanes
@@ -262,7 +253,7 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
         h->fpw = 32 / (LP * S);
     }
     const int gmax = h->fast ? n - 4 : n - 1;
-    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 8704 : 9216);
+    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 8192 : 9216);
     int G = env_int("PCL_POLAR_G", -1);
     const int gmin = h->fast ? 1 : 0;
     if (G < 0) {

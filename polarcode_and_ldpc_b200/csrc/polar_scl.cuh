@@ -48,9 +48,7 @@ struct PolarLayout {
     // per-warp shared memory byte offsets
     int off_cm, off_newpm, off_sel, off_llr, off_bw, off_uw, warp_bytes;
     int uw_slots;        // 1, or LP when CRC selection needs every path's u
-    int gbw;             // fast kernel: left arrays of levels 1..gbw live in the global scratch
-    int64_t scratch_llr_per_warp;  // reals of LLR-level scratch per resident warp
-    int64_t scratch_per_warp;      // reals of global scratch per resident warp (LLR levels + left arrays)
+    int64_t scratch_per_warp;  // reals of global scratch per resident warp
 };
 
 template <typename real>

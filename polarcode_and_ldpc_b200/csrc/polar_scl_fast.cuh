@@ -208,17 +208,9 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
     double* newpm = (double*)(wsm + Y.off_newpm) + cbase;
     int* sel = (int*)(wsm + Y.off_sel) + cbase;
     real* sl = (real*)(wsm + Y.off_llr);          // levels max(G,1)+1 .. n-4, [k][col]
-    uint32_t* bw = (uint32_t*)(wsm + Y.off_bw);   // big left levels GBW+1 .. nb, [w][col]
+    uint32_t* bw = (uint32_t*)(wsm + Y.off_bw);   // big left levels 1 .. nb, [w][col]
     uint32_t* uw = (uint32_t*)(wsm + Y.off_uw);   // final u words
     real* gl = P.scratch + (int64_t)(blockIdx.x * wpb + warp) * Y.scratch_per_warp;
-    // The bit-packed left arrays of the top GBW levels (written 1-2 times per frame) live behind
-    // the LLR levels in the same scratch; that frees shared memory for one more LLR level.
-    const int GBW = Y.gbw;
-    uint32_t* gbw = (uint32_t*)(gl + Y.scratch_llr_per_warp);
-    auto bwlevel = [&](int d) -> uint32_t* {      // base of the left array of level d, [w][col]
-        return (d <= GBW) ? gbw + LPF * ((N >> 5) - (N >> (d + 4)))
-                          : bw + LPF * ((N >> (5 + GBW)) - (N >> (d + 4)));
-    };
 
     const double NEG_INF = -(double)pcl_math<real>::inf();
     const double DEAD = -1.0e300;                 // key of an inactive slot (sorts last, stays finite)
@@ -249,7 +241,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
             const int start = (blk == 0) ? 1 : n - (__ffs(i0) - 1);
             const int dfirst = (n - 3 >= 2) ? 2 : 1;
             const int bit1 = (i0 >> (n - 1)) & 1;
-            const uint32_t* b1src = bwlevel(1) + cbase + (ptrB & (LP - 1));   // left array of level 1 (nb >= 1)
+            const uint32_t* b1src = bw + cbase + (ptrB & (LP - 1));      // left array of level 1 (nb >= 1)
             auto lvl1 = [&](int m) -> real {
                 const int r = (int)(__brev((unsigned)m) >> (32 - n));      // even: the pair is one aligned load
                 real y0, y1;
@@ -273,7 +265,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                 }
                 const uint32_t* bsrc = nullptr;
                 if (bit && d <= nb)
-                    bsrc = bwlevel(d) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
+                    bsrc = bw + LPF * ((N >> 5) - (N >> (d + 4))) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
                 const uint32_t smf = small >> ((32 - 2 * sz) & 31);        // small-field partial sums of level d
                 if (d < n - 3) {
                     real* dst = ((d <= G) ? gl + (int64_t)LPF * ((N >> 1) - (N >> (d - 1)))
@@ -535,7 +527,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                                 } else {
                                     const int d = n - 5;
                                     if (act) {
-                                        if (kk == 0) bwlevel(d)[col] = c;
+                                        if (kk == 0) bw[LPF * ((N >> 5) - (N >> (d + 4))) + col] = c;
                                         ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
                                     }
                                     __syncwarp();
@@ -544,13 +536,13 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                                 const int cto = __ffs(~i) - 1;
                                 const int d = n - cto;
                                 const int Wd = N >> (d + 5);
-                                uint32_t* dest = bwlevel(d);
+                                uint32_t* dest = bw + LPF * ((N >> 5) - (N >> (d + 4)));
                                 if (act && kk == 0) dest[(Wd - 1) * LPF + col] = c;
                                 __syncwarp();
                                 for (int l = n - 5; l > d; l--) {
                                     const int w = N >> (l + 5);
                                     const int ql = cbase + ((ptrB >> ((l - 1) * PB)) & (LP - 1));
-                                    const uint32_t* lsrc = bwlevel(l);
+                                    const uint32_t* lsrc = bw + LPF * ((N >> 5) - (N >> (l + 4)));
                                     if (act)
                                         for (int jw = kk; jw < w; jw += S)
                                             dest[(Wd - 2 * w + jw) * LPF + col] =
@@ -600,7 +592,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                         const int Wl = 1 << (31 - __clz(r - 1));
                         const int l = (31 - __clz(NW)) - (31 - __clz(Wl));
                         const int jw = w - (NW - 2 * Wl);
-                        v = bwlevel(l)[jw * LPF + fq * LP + ((pB >> ((l - 1) * PB)) & (LP - 1))];
+                        v = bw[LPF * ((N >> 5) - (N >> (l + 4))) + jw * LPF + fq * LP + ((pB >> ((l - 1) * PB)) & (LP - 1))];
                         v ^= (v >> 1) & 0x55555555u;
                         v ^= (v >> 2) & 0x33333333u;
                         v ^= (v >> 4) & 0x0F0F0F0Fu;
