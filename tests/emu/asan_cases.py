@@ -1,0 +1,24 @@
+import sys, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np, ctypes
+from tests.emu import emu
+emu.LIB=os.environ.get('PCL_EMU_LIB','/tmp/libpcl_emu_asan.so')
+emu._lib=ctypes.CDLL(emu.LIB); emu._lib.pcl_last_error.restype=ctypes.c_char_p; emu._lib.simt_set_reverse.argtypes=[ctypes.c_int]
+from oracle import oracle
+import polarcode_and_ldpc_b200 as P
+rng=np.random.default_rng(0)
+for N,K,L,F in ((256,128,8,5),(64,32,32,3),(1024,512,8,2),(16,8,4,9),(128,64,2,19)):
+    fz=P.bhattacharyya_frozen_set(N,K,2.0); llr=rng.normal(1,3,size=(F,N))
+    ref=oracle.polar_scl(N,L,fz,llr)
+    for S in (1,2):
+        for dt in ('f32','f64'):
+            got=emu.polar_decode(N,K,L,fz,llr,dt,want_pm=True,want_leaf=True,env={'PCL_POLAR_S':S})[0]
+            assert np.array_equal(got,ref),(N,L,S,dt)
+    got=emu.polar_decode(N,K,L,fz,llr,'f64',crc=(0x1D,8)); 
+    got=emu.polar_decode(N,K,L,fz,llr,'f64',env={'PCL_POLAR_GENERIC':1}); assert np.array_equal(got,ref)
+for n in (96,504):
+    H=P.gallager_parity_check(n,3,6,42); llr=rng.normal(1,2.5,size=(4,n))
+    for mode in ('bp','ms'):
+        for dt in ('f32','f64'):
+            emu.ldpc_decode(H,llr,mode,6,0.75,True,dt,want_total=True)
+Hm=P.mackay_parity_check(120,60,3,6,seed=42); emu.ldpc_decode(Hm,rng.normal(1,2,size=(3,120)),'bp',5)
+print('asan run ok')

@@ -378,3 +378,22 @@ def test_lanes_per_path_variants(S):
                 assert bad == 0 if dt == "float64" else bad <= 1, f"N={N} L={L} S={S} {dt}: {bad} frames differ"
     finally:
         os.environ.pop("PCL_POLAR_S")
+
+
+def test_large_codes():
+    """Sizes beyond the BASELINE configs (benchmarks/test_code_parameters.py:33-36 goes to
+    N = 4096 / n = 4032): more tree levels in the L2 scratch, more partial-sum words."""
+    for N, K, L, F in ((4096, 2048, 4, 96), (8192, 4096, 2, 40), (4096, 3000, 8, 33)):
+        frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+        _, llr = _polar_frames(N, K, frozen, F, 1.0, N + L)
+        ref = oracle.polar_scl(N, L, frozen, llr, nthreads=8)
+        assert np.array_equal(P.SCLDecoder(N, K, L, frozen, dtype="float64").decode_batch(llr), ref), (N, L)
+        assert int((P.SCLDecoder(N, K, L, frozen).decode_batch(llr) != ref).any(axis=1).sum()) <= 1
+    H = P.gallager_parity_check(4032, 3, 6, 42)
+    np.random.seed(4)
+    llr = P.AWGNChannel(0.5).transmit_batch(np.zeros((64, 4032), dtype=int))
+    rb, ri = oracle.ldpc(H, llr, "bp", max_iter=20, nthreads=8)
+    b, it = P.BPDecoder(H, max_iter=20, dtype="float64").decode_batch(llr, return_iterations=True)
+    assert np.array_equal(b, rb) and np.array_equal(it, ri)
+    b, it = P.BPDecoder(H, max_iter=20).decode_batch(llr, return_iterations=True)
+    assert int(((b != rb).any(axis=1) | (it != ri)).sum()) <= 1
