@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: decoded information-bit throughput (Gbps) of the batched decoders.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl8|bp504|sc256|scl32|ms2016]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scl8|bp504|bp504es|sc256|scl32|ms2016]
     python bench.py --impl reference ...      # CPU arm: the oracle port on all host cores
 
 One "step" = one pass of the decode hot path over one batch of synthetic AWGN frames.
@@ -46,6 +46,8 @@ WORKLOADS = {
                   desc="Polar SC N=256 K=128, AWGN 3 dB (BASELINE configs[0])"),
     "bp504": dict(kind="ldpc", n=504, k=252, mode="bp", iters=20, snr=1.0, frames=262144,
                   desc="LDPC BP n=504 (3,6) Gallager H seed 42, 20 iterations, early_stop off (BASELINE configs[2])"),
+    "bp504es": dict(kind="ldpc", n=504, k=252, mode="bp", iters=20, snr=1.0, frames=262144, early_stop=True,
+                    desc="LDPC BP n=504, max_iter=20 WITH syndrome early stop at 1 dB (mean ~3 iterations)"),
     "ms2016": dict(kind="ldpc", n=2016, k=1008, mode="ms", iters=20, snr=1.0, frames=65536,
                    desc="LDPC Min-Sum(0.75) n=2016 (3,6), 20 iterations, early_stop off (BASELINE configs[3])"),
 }
@@ -164,7 +166,7 @@ def make_decoder(w, code, dtype="float32"):
             return P.SCDecoder(w["N"], w["K"], frozen_bits=code["frozen"], dtype=dtype)
         return P.SCLDecoder(w["N"], w["K"], list_size=w["L"], frozen_bits=code["frozen"], dtype=dtype)
     if w["mode"] == "bp":
-        return P.BPDecoder(code["H"], max_iter=w["iters"], early_stop=False, dtype=dtype)
+        return P.BPDecoder(code["H"], max_iter=w["iters"], early_stop=bool(w.get("early_stop", False)), dtype=dtype)
     return P.MSDecoder(code["H"], max_iter=w["iters"], normalization=0.75, early_stop=False, dtype=dtype)
 
 
