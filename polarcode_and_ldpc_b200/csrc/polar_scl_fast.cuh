@@ -1,21 +1,30 @@
-// polar_scl_fast.cuh -- SC / SCL decoder, one warp per frame, register-resident tree bottom.
+// polar_scl_fast.cuh -- SC / SCL decoder with a register-resident tree bottom and several
+// frames per warp.  Production kernel for N >= 16 (polar_scl.cuh is the fallback).
 //
-// Same algorithm, list semantics and memory layout as polar_scl.cuh (read that header
-// first); what changes is where the work of the lowest three tree levels happens.  The
-// generic kernel was issue-bound (ncu: 515 k warp instructions per N=1024 L=8 frame, 3.0
-// IPC): 7 of every 8 level visits touch a node of <= 4 LLRs per path and paid loop,
-// address and packed-pointer arithmetic plus a shared-memory round trip each.  Here the
-// tree is cut at height 3: the decoder walks N/8 blocks of 8 leaves.
-//   * levels above the cut (node size >= 16) -- unchanged: [k][slot] arrays in shared
-//     memory / L2 scratch, lazily shared between paths through packed slot pointers;
-//   * the block root (8 LLRs per path) is produced straight into registers, and the
-//     levels of size 4, 2, 1 below it live in registers of the S = 32/LP lanes that own
-//     the path.  Butterflies whose two operands sit in the same lane are plain register
-//     ops; the others take one shuffle.  The 8 leaves are fully unrolled, so every stage,
-//     partial-sum bit position and live-register set is a compile-time constant;
-//   * a surviving path inherits its parent's live registers with shuffles (2 on average)
-//     together with ONE packed 64-bit pointer word (LLR levels low half, partial-sum
-//     levels high half) and the 32-bit small partial-sum word.
+// Same algorithm, list semantics and pointer scheme as polar_scl.cuh (read that header
+// first).  What changed, each step driven by an ncu capture (profiles/r01a .. r01h):
+//   * The generic kernel was issue-bound (515 k warp instructions per N=1024 L=8 frame):
+//     7 of every 8 level visits touch a node of <= 4 LLRs per path and paid loop, address and
+//     packed-pointer arithmetic plus a shared-memory round trip each.  Here the tree is cut at
+//     height 3: the decoder walks N/8 blocks of 8 leaves; the block root (8 LLRs per path) is
+//     produced straight into registers and the levels of size 4, 2, 1 below it stay in
+//     registers.  The leaf loop is rolled (an unrolled body overflowed the instruction cache);
+//     f / g per stage is still a compile-time choice behind three uniform branches on j.
+//   * S lanes own a path and a warp decodes FPW = 32 / (LP * S) frames side by side
+//     (default S = 1: a lane owns a whole path, 4 frames per warp at L = 8).  All frames of a
+//     warp follow the same schedule (frozen pattern, number of live paths), so every branch is
+//     warp-uniform and the per-leaf bookkeeping instructions are shared by FPW frames.
+//   * A surviving path inherits its parent's live registers with shuffles (only those a later
+//     leaf of the block still reads) together with two packed 32-bit pointer words (LLR levels,
+//     partial-sum levels) and the 32-bit small partial-sum word.
+//   * Level 1 is never stored: level 2 recomputes its two level-1 operands from ONE aligned
+//     4-element channel load, walked in bit-reversed order so the loads are sequential.
+//     Levels 2..G live in an L2/HBM scratch and are streamed in software-pipelined batches of
+//     UNR independent row loads; levels G+1..n-4 stay in shared memory ([k][column] layout:
+//     conflict free / fully coalesced).
+//   * Prune: all-pairs rank.  fp32 build: the candidate id replaces the lowest mantissa bits of
+//     the fp64 metric, so one DSETP + one predicated add per pair gives both the metric order
+//     and the reference's tie order; fp64 build keeps the exact two-key comparison.
 // Path metric in fp64; fp32 build evaluates log1p(exp(-|x|)) as 2 atanh(u / (2 + u)) with
 // u = 2^(-|x| log2 e) (one ex2, one rcp, 6 FMA; |error| < 1e-7).
 #pragma once
