@@ -321,14 +321,30 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
 #define PCL_POLAR_UNR 8
 #endif
                             constexpr int UNR = (S >= 4 && PCL_POLAR_UNR > 4) ? 4 : PCL_POLAR_UNR;
+                            constexpr int STEP = 32 * UNR;
                             real a[UNR], b[UNR], a2[UNR], b2[UNR];
+                            // compute + store one batch whose operands are already in registers
+                            auto emit = [&](const real* av, const real* bv, int o0) {
+                                if (bit) {
+                                    const int k0 = kk + S * (o0 >> 5);          // k of element e: k0 + S e
+                                    const uint32_t wbits = (d <= nb) ? bsrc[(k0 >> 5) * LPF] >> (k0 & 31) : smf >> k0;
+#pragma unroll
+                                    for (int e = 0; e < UNR; e++)
+                                        dst[o0 + 32 * e] = pcl_fast<real>::g(av[e], bv[e], (wbits >> (S * e)) & 1u);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < UNR; e++) dst[o0 + 32 * e] = pcl_math<real>::f(av[e], bv[e]);
+                                }
+                            };
 #pragma unroll
                             for (int e = 0; e < UNR; e++) {
                                 a[e] = src[32 * e];
                                 b[e] = src[32 * e + hi];
                             }
-                            for (int o0 = 0; o0 < hi; o0 += 32 * UNR) {
-                                const int o1 = o0 + 32 * UNR;
+                            // ping-pong between two register sets: the loads of the next batch are in
+                            // flight while the current one is computed, without register moves
+                            for (int o0 = 0; o0 < hi; o0 += 2 * STEP) {
+                                const int o1 = o0 + STEP, o2 = o0 + 2 * STEP;
                                 if (o1 < hi) {
 #pragma unroll
                                     for (int e = 0; e < UNR; e++) {
@@ -336,18 +352,17 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                                         b2[e] = src[o1 + 32 * e + hi];
                                     }
                                 }
-                                if (bit) {
-                                    const int k0 = kk + S * (o0 >> 5);          // k of element e: k0 + S e
-                                    const uint32_t wbits = (d <= nb) ? bsrc[(k0 >> 5) * LPF] >> (k0 & 31) : smf >> k0;
+                                emit(a, b, o0);
+                                if (o1 < hi) {
+                                    if (o2 < hi) {
 #pragma unroll
-                                    for (int e = 0; e < UNR; e++)
-                                        dst[o0 + 32 * e] = pcl_fast<real>::g(a[e], b[e], (wbits >> (S * e)) & 1u);
-                                } else {
-#pragma unroll
-                                    for (int e = 0; e < UNR; e++) dst[o0 + 32 * e] = pcl_math<real>::f(a[e], b[e]);
+                                        for (int e = 0; e < UNR; e++) {
+                                            a[e] = src[o2 + 32 * e];
+                                            b[e] = src[o2 + 32 * e + hi];
+                                        }
+                                    }
+                                    emit(a2, b2, o1);
                                 }
-#pragma unroll
-                                for (int e = 0; e < UNR; e++) { a[e] = a2[e]; b[e] = b2[e]; }
                             }
                         }
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
