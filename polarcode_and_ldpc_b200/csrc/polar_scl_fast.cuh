@@ -159,6 +159,24 @@ PCL_DEVICE void pcl_load_quad<double>(const double* ptr, double* v)
 }
 
 template <typename real>
+PCL_DEVICE void pcl_store_quad(real* ptr, const real* v);
+template <>
+PCL_DEVICE void pcl_store_quad<float>(float* ptr, const float* v)
+{
+    float4 q;
+    q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = v[3];
+    *reinterpret_cast<float4*>(ptr) = q;
+}
+template <>
+PCL_DEVICE void pcl_store_quad<double>(double* ptr, const double* v)
+{
+    double2 q0, q1;
+    q0.x = v[0]; q0.y = v[1]; q1.x = v[2]; q1.y = v[3];
+    *reinterpret_cast<double2*>(ptr) = q0;
+    *reinterpret_cast<double2*>(ptr + 2) = q1;
+}
+
+template <typename real>
 PCL_DEVICE void pcl_load_pair(const real* ptr, real& a, real& b);
 template <>
 PCL_DEVICE void pcl_load_pair<float>(const float* ptr, float& a, float& b)
@@ -191,6 +209,9 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
     constexpr int FPW = LPF / LP;                // frames per warp
     constexpr int NC = 2 * LP;                   // prune candidates per frame
     constexpr bool EXACT = sizeof(real) == 8;
+    // S == 1: stored levels use the layout [k / 4][column][k % 4], so a lane moves four
+    // consecutive elements of its path with one 16-byte access (a warp: 512 contiguous bytes)
+    constexpr bool VEC = (S == 1);
     constexpr int E3 = (8 >= S) ? 8 / S : 1;     // registers per lane for the size-8 level
     constexpr int E2 = (4 >= S) ? 4 / S : 1;
     constexpr int E1 = (2 >= S) ? 2 / S : 1;
@@ -270,7 +291,8 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                 if (d > 2) {
                     const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
                     src = ((d - 1 <= G) ? gl + (int64_t)LPF * ((N >> 1) - (N >> (d - 2)))
-                                        : sl + LPF * ((N >> G) - (N >> (d - 2)))) + kk * LPF + cbase + q;
+                                        : sl + LPF * ((N >> G) - (N >> (d - 2)))) +
+                          (VEC ? 4 * (cbase + q) : kk * LPF + cbase + q);
                 }
                 const uint32_t* bsrc = nullptr;
                 if (bit && d <= nb)
@@ -278,10 +300,94 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                 const uint32_t smf = small >> ((32 - 2 * sz) & 31);        // small-field partial sums of level d
                 if (d < n - 3) {
                     real* dst = ((d <= G) ? gl + (int64_t)LPF * ((N >> 1) - (N >> (d - 1)))
-                                          : sl + LPF * ((N >> G) - (N >> (d - 1)))) + kk * LPF + col;
+                                          : sl + LPF * ((N >> G) - (N >> (d - 1)))) + (VEC ? 4 * col : kk * LPF + col);
                     // element k = kk + S t sits at word offset 32 t of the [k][col] array
                     if (act) {
-                        if (d == 2) {
+                        if (d == 2 && VEC) {
+                            // quad i4 of level 2 = elements 4 i4 + r; element k comes from the 4 channel
+                            // values at 4 br(k), and br(4 i4 + r) = br(i4) + br2(r) * sz/4: four sequential
+                            // streams of 16-byte loads, one 16-byte store
+                            const int nq = sz >> 2;
+#pragma unroll 2
+                            for (int tl = 0; tl < nq; tl++) {
+                                const int i4 = (int)(__brev((unsigned)tl) >> (36 - n));    // (n-4)-bit reversal
+                                real yv[4][4];
+#pragma unroll
+                                for (int mm = 0; mm < 4; mm++) pcl_load_quad<real>(y + 4 * (tl + mm * nq), yv[mm]);
+                                const int k4 = 4 * i4;
+                                uint32_t n1 = 0, n2 = 0, n0 = 0;
+                                if (bit1) {
+                                    if (nb >= 1) {
+                                        n1 = b1src[(k4 >> 5) * LPF] >> (k4 & 31);
+                                        n2 = b1src[((k4 + sz) >> 5) * LPF] >> ((k4 + sz) & 31);
+                                    } else {
+                                        n1 = small >> ((32 - N + k4) & 31);
+                                        n2 = small >> ((32 - N + k4 + sz) & 31);
+                                    }
+                                }
+                                if (bit) n0 = (d <= nb) ? bsrc[(k4 >> 5) * LPF] >> (k4 & 31) : smf >> k4;
+                                real out[4];
+#pragma unroll
+                                for (int mm = 0; mm < 4; mm++) {
+                                    const int r = ((mm & 1) << 1) | (mm >> 1);             // 2-bit reversal
+                                    real a, b;
+                                    if (bit1) {
+                                        a = pcl_fast<real>::g(yv[mm][0], yv[mm][1], (n1 >> r) & 1u);
+                                        b = pcl_fast<real>::g(yv[mm][2], yv[mm][3], (n2 >> r) & 1u);
+                                    } else {
+                                        a = pcl_math<real>::f(yv[mm][0], yv[mm][1]);
+                                        b = pcl_math<real>::f(yv[mm][2], yv[mm][3]);
+                                    }
+                                    out[r] = bit ? pcl_fast<real>::g(a, b, (n0 >> r) & 1u) : pcl_math<real>::f(a, b);
+                                }
+                                pcl_store_quad<real>(dst + i4 * 128, out);
+                            }
+                        } else if (VEC) {
+                            // quads of 4 consecutive elements, two quads per batch, ping-pong register sets
+                            const int nq = sz >> 2;                              // quads per half
+                            real a[2][4], b[2][4], a2[2][4], b2[2][4];
+                            auto emitq = [&](real (*av)[4], real (*bv)[4], int i) {
+#pragma unroll
+                                for (int u = 0; u < 2; u++) {
+                                    real out[4];
+                                    if (bit) {
+                                        const int k4 = 4 * (i + u);
+                                        const uint32_t nbits = (d <= nb) ? bsrc[(k4 >> 5) * LPF] >> (k4 & 31) : smf >> k4;
+#pragma unroll
+                                        for (int e = 0; e < 4; e++) out[e] = pcl_fast<real>::g(av[u][e], bv[u][e], (nbits >> e) & 1u);
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < 4; e++) out[e] = pcl_math<real>::f(av[u][e], bv[u][e]);
+                                    }
+                                    pcl_store_quad<real>(dst + (i + u) * 128, out);
+                                }
+                            };
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                pcl_load_quad<real>(src + u * 128, a[u]);
+                                pcl_load_quad<real>(src + (u + nq) * 128, b[u]);
+                            }
+                            for (int i = 0; i < nq; i += 4) {
+                                if (i + 2 < nq) {
+#pragma unroll
+                                    for (int u = 0; u < 2; u++) {
+                                        pcl_load_quad<real>(src + (i + 2 + u) * 128, a2[u]);
+                                        pcl_load_quad<real>(src + (i + 2 + u + nq) * 128, b2[u]);
+                                    }
+                                }
+                                emitq(a, b, i);
+                                if (i + 2 < nq) {
+                                    if (i + 4 < nq) {
+#pragma unroll
+                                        for (int u = 0; u < 2; u++) {
+                                            pcl_load_quad<real>(src + (i + 4 + u) * 128, a[u]);
+                                            pcl_load_quad<real>(src + (i + 4 + u + nq) * 128, b[u]);
+                                        }
+                                    }
+                                    emitq(a2, b2, i + 2);
+                                }
+                            }
+                        } else if (d == 2) {
                             // Level-2 element k needs level-1 elements k and k + N/4, i.e. the channel
                             // pairs at br(k) and br(k) + 2: ONE aligned 4-element load.  Walking t = br(k)
                             // upwards makes those loads sequential in memory.
@@ -381,6 +487,9 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                             } else if (d == 2) {
                                 a = lvl1(k);
                                 b = lvl1(k + 8);
+                            } else if (VEC) {
+                                a = src[(t >> 2) * 128 + (t & 3)];           // level n-4: quads 0,1 | 2,3
+                                b = src[((t >> 2) + 2) * 128 + (t & 3)];
                             } else {
                                 a = src[32 * t];
                                 b = src[32 * t + 8 * LPF];
