@@ -474,6 +474,20 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
                     }
                     __syncwarp();
+                } else if (act && VEC && d > 2) {      // d == n-3 from four 16-byte loads of level n-4
+                    real qa[2][4], qb[2][4];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        pcl_load_quad<real>(src + u * 128, qa[u]);
+                        pcl_load_quad<real>(src + (u + 2) * 128, qb[u]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < E3; t++) {
+                        const real a = qa[(t >> 2) & 1][t & 3], b = qb[(t >> 2) & 1][t & 3];
+                        const real vg = pcl_fast<real>::g(a, b, (small >> (16 + t)) & 1u);
+                        const real vf = pcl_math<real>::f(a, b);
+                        R3[t] = bit ? vg : vf;
+                    }
                 } else if (act) {                 // d == n-3: sz == 8, straight into registers
 #pragma unroll
                     for (int t = 0; t < E3; t++) {
