@@ -595,15 +595,17 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                         cm[LP + p] = kb;
                         __syncwarp();
                         int ra = 0, rb = 0;
-#pragma unroll 16
-                        for (int jj = 0; jj < NC; jj++) {
-                            const double kj = cm[jj];
+#pragma unroll 8
+                        for (int jj = 0; jj < NC; jj += 2) {
+                            const double2 kp = *reinterpret_cast<const double2*>(cm + jj);   // 16-byte aligned
                             if (EXACT) {
-                                ra += pcl_beats<EXACT>(kj, ka, jj, p);
-                                rb += pcl_beats<EXACT>(kj, kb, jj, LP + p);
+                                ra += pcl_beats<EXACT>(kp.x, ka, jj, p) + pcl_beats<EXACT>(kp.y, ka, jj + 1, p);
+                                rb += pcl_beats<EXACT>(kp.x, kb, jj, LP + p) + pcl_beats<EXACT>(kp.y, kb, jj + 1, LP + p);
                             } else {
-                                pcl_rank_acc(ra, kj, ka);
-                                pcl_rank_acc(rb, kj, kb);
+                                pcl_rank_acc(ra, kp.x, ka);
+                                pcl_rank_acc(rb, kp.x, kb);
+                                pcl_rank_acc(ra, kp.y, ka);
+                                pcl_rank_acc(rb, kp.y, kb);
                             }
                         }
                         if (ra < ns) { sel[ra] = p; newpm[ra] = mca; }
