@@ -198,7 +198,7 @@ PCL_DEVICE void pcl_load_pair<double>(const double* ptr, double& a, double& b)
 // schedule (frozen pattern, number of live paths), so every branch stays warp-uniform and
 // the per-leaf bookkeeping instructions are shared by FPW frames.
 #ifndef PCL_POLAR_MINB
-#define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for
+#define PCL_POLAR_MINB 5      // resident 128-thread blocks per SM the register allocation aims for (96 regs)
 #endif
 template <int LP, int S, typename real>
 __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3) polar_scl_fast_kernel(PolarParams<real> P)
