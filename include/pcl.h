@@ -73,8 +73,8 @@ int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8
 int pcl_polar_lp(const pcl_polar_t* h);
 /* Launch geometry of the last decode (for gpu_launches / occupancy reporting): grid, block,
  * dynamic shared memory, number of tree levels kept in the L2 scratch, and the kernel in use:
- * 0 = generic kernel, S > 0 = register-resident-bottom kernel with S lanes per path
- * (32 / (LP * S) frames per warp). */
+ * 0 = generic kernel, 1 = register-resident-bottom kernel (a lane owns a path, 32 / LP frames
+ * per warp), 2 = the same with log2 N and the level split compiled in as constants. */
 int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
                           int* fast);
 

@@ -105,7 +105,8 @@ struct pcl_polar {
     int wpb, grid_max, smem_bytes;
     int last_grid = 0;
     int fast = 0;               // register-resident tree bottom (polar_scl_fast.cuh)
-    int S = 1, fpw = 1;         // fast kernel: lanes per path, frames per warp
+    int fpw = 1;                // fast kernel: frames per warp
+    int NL = 0, GL = 0;         // fast kernel: compiled-in log2 N and G (0: run-time values)
     // host-buffer pipeline
     void* d_llr[PCL_NSTAGE] = {};
     uint8_t* d_bits[PCL_NSTAGE] = {};
@@ -127,8 +128,14 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
     Y.nb = Y.n > 5 ? Y.n - 5 : 0;
     Y.uw_slots = crc ? cols : fpw;
     int off = 0;
-    Y.off_cm = off;     off += (2 * cols + 2 * fpw) * 8;       // per frame: 2 LP keys + 2 pad (bank spread)
-    Y.off_newpm = off;  off += cols * 8;
+    if (fast) {
+        // one prune scratch block per frame of the warp (pcl_fast_frame_bytes)
+        Y.off_cm = off;     off += fpw * pcl_fast_frame_bytes(LP);
+        Y.off_newpm = off;
+    } else {
+        Y.off_cm = off;     off += (2 * cols + 2 * fpw) * 8;   // per frame: 2 LP keys + 2 pad (bank spread)
+        Y.off_newpm = off;  off += cols * 8;
+    }
     // generic kernel keeps levels G+1 .. n-1 in shared memory, the fast one G+1 .. n-4
     // (the fast kernel never stores level 1, so its G is at least 1)
     int llr_vals = fast ? ((G >= Y.n - 4) ? 0 : cols * ((N >> G) - 16))
@@ -142,14 +149,16 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
                               : (int64_t)cols * (N - (N >> G));           // levels 1 .. G
 }
 
-// Kernel variants.  Generic: one frame per warp, every level in shared memory.  Fast: S lanes
-// per path, 32 / (LP * S) frames per warp (polar_scl_fast.cuh).
+// Kernel variants.  Generic: one frame per warp, every level in shared memory.  Fast: a lane
+// owns a path, 32 / LP frames per warp (polar_scl_fast.cuh); X(LP, log2 N, G) with log2 N = 0
+// for the run-time code length, else the code length and G compiled in as constants.
 #define PCL_POLAR_FAST_VARIANTS(X) \
-    X(1, 1) X(1, 2) X(2, 1) X(2, 2) X(4, 1) X(4, 2) X(8, 1) X(8, 2) X(8, 4) X(16, 1) X(16, 2) X(32, 1)
+    X(1, 0, 0) X(2, 0, 0) X(4, 0, 0) X(8, 0, 0) X(16, 0, 0) X(32, 0, 0) \
+    X(1, 10, 5) X(8, 10, 5) X(32, 10, 5) X(1, 8, 2) X(8, 8, 2)
 
-static bool polar_fast_variant_exists(int LP, int S)
+static bool polar_fast_variant_exists(int LP, int nl, int gl)
 {
-#define X(lp, s) if (LP == lp && S == s) return true;
+#define X(lp, n_, g_) if (LP == lp && nl == n_ && gl == g_) return true;
     PCL_POLAR_FAST_VARIANTS(X)
 #undef X
     return false;
@@ -159,7 +168,7 @@ template <typename real, typename Fn>
 static int polar_with_kernel(pcl_polar* h, Fn&& fn)
 {
     if (h->fast) {
-#define X(lp, s) if (h->LP == lp && h->S == s) return fn(polar_scl_fast_kernel<lp, s, real>);
+#define X(lp, n_, g_) if (h->LP == lp && h->NL == n_ && h->GL == g_) return fn(polar_scl_fast_kernel<lp, real, n_, g_>);
         PCL_POLAR_FAST_VARIANTS(X)
 #undef X
     } else {
@@ -243,15 +252,9 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     while ((1 << pb) < LP) pb++;
     h->fast = (n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 &&
                env_int("PCL_POLAR_GENERIC", 0) == 0) ? 1 : 0;
-    h->S = 1; h->fpw = 1;
-    if (h->fast) {
-        // S = 1: a lane owns a whole path, 32 / LP frames share a warp's instruction stream
-        // (measured best on B200 for L = 8: 3.7 Gbps vs 2.9 (S = 2) and 2.0 (S = 4)).
-        int S = env_int("PCL_POLAR_S", 1);
-        if (!polar_fast_variant_exists(LP, S)) S = 1;
-        h->S = S;
-        h->fpw = 32 / (LP * S);
-    }
+    // a lane owns a whole path, 32 / LP frames share a warp's instruction stream (measured best
+    // on B200 for L = 8: 3.7 Gbps vs 2.9 / 2.0 with 2 / 4 lanes per path, profiles/r01d, r01e)
+    h->fpw = h->fast ? 32 / LP : 1;
     const int gmax = h->fast ? n - 4 : n - 1;
     int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 8192 : 9216);
     int G = env_int("PCL_POLAR_G", -1);
@@ -265,6 +268,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     if (G > gmax) G = gmax;
     if (G < gmin) G = gmin;
     polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
+    h->NL = 0; h->GL = 0;
+    if (h->fast && env_int("PCL_POLAR_NL", 1) != 0 && polar_fast_variant_exists(LP, n, G)) { h->NL = n; h->GL = G; }
     h->smem_bytes = h->lay.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
         delete h;
@@ -322,7 +327,7 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
                                      int* fast)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
-    if (fast) *fast = h->fast ? h->S : 0;
+    if (fast) *fast = h->fast ? (h->NL ? 2 : 1) : 0;
     if (grid) *grid = h->last_grid;
     if (block) *block = h->wpb * 32;
     if (smem_bytes) *smem_bytes = h->smem_bytes;

@@ -17,9 +17,11 @@
 
 #ifdef PCL_EMU
 #define PCL_DEVICE inline
+#define PCL_HOST_DEVICE inline
 __device__ inline unsigned char* pcl_dyn_smem() { return simt::dyn_smem(); }
 #else
 #define PCL_DEVICE __device__ __forceinline__
+#define PCL_HOST_DEVICE __host__ __device__ inline
 __device__ __forceinline__ unsigned char* pcl_dyn_smem()
 {
     extern __shared__ __align__(16) unsigned char pcl_smem_raw[];

@@ -1,4 +1,4 @@
-"""Time decode_batch for list sizes x lanes-per-path variants (PCL_POLAR_S) on one GPU."""
+"""Time decode_batch for list sizes x compiled / run-time code length variants (PCL_POLAR_NL) on one GPU."""
 import os
 import sys
 
@@ -14,10 +14,8 @@ for N, K, L, F in ((256, 128, 1, 524288), (1024, 512, 1, 262144), (1024, 512, 2,
                    (1024, 512, 8, 131072), (1024, 512, 16, 65536), (1024, 512, 32, 32768)):
     w = dict(kind="polar", N=N, K=K, L=L, snr=2.0, frames=F)
     llr, ref, code = bench.make_inputs(w, torch, dev, 1)
-    for S in (1, 2, 4):
-        if L * S > 32 or (S == 4 and L != 8):
-            continue
-        os.environ["PCL_POLAR_S"] = str(S)
+    for S in (1, 0):
+        os.environ["PCL_POLAR_NL"] = str(S)
         dec = P.SCDecoder(N, K, frozen_bits=code["frozen"]) if L == 1 else P.SCLDecoder(N, K, L, code["frozen"])
         for _ in range(2):
             bits = dec.decode_batch(llr)
@@ -30,5 +28,5 @@ for N, K, L, F in ((256, 128, 1, 524288), (1024, 512, 1, 262144), (1024, 512, 2,
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         ok = (bits == ref).all(dim=1).float().mean().item()
-        print(f"N={N} L={L} S={S} {F * K / ms / 1e6:8.3f} Gbps  {F / ms / 1e3:8.2f} Mframes/s  frame-ok {ok:.4f} {dec.launch_info()}", flush=True)
+        print(f"N={N} L={L} NL={S} {F * K / ms / 1e6:8.3f} Gbps  {F / ms / 1e3:8.2f} Mframes/s  frame-ok {ok:.4f} {dec.launch_info()}", flush=True)
         del dec

@@ -9,9 +9,9 @@ rng=np.random.default_rng(0)
 for N,K,L,F in ((256,128,8,5),(64,32,32,3),(1024,512,8,2),(16,8,4,9),(128,64,2,19)):
     fz=P.bhattacharyya_frozen_set(N,K,2.0); llr=rng.normal(1,3,size=(F,N))
     ref=oracle.polar_scl(N,L,fz,llr)
-    for S in (1,2):
+    for S in (1,0):
         for dt in ('f32','f64'):
-            got=emu.polar_decode(N,K,L,fz,llr,dt,want_pm=True,want_leaf=True,env={'PCL_POLAR_S':S})[0]
+            got=emu.polar_decode(N,K,L,fz,llr,dt,want_pm=True,want_leaf=True,env={'PCL_POLAR_NL':S})[0]
             assert np.array_equal(got,ref),(N,L,S,dt)
     got=emu.polar_decode(N,K,L,fz,llr,'f64',crc=(0x1D,8)); 
     got=emu.polar_decode(N,K,L,fz,llr,'f64',env={'PCL_POLAR_GENERIC':1}); assert np.array_equal(got,ref)

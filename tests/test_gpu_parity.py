@@ -361,13 +361,18 @@ def test_generic_kernel_fallback_matches(golden_dir):
         "polar_scl_fast_kernel"
 
 
-@pytest.mark.parametrize("S", [1, 2, 4])
-def test_lanes_per_path_variants(S):
-    """PCL_POLAR_S selects how many lanes share a path (and hence how many frames share a warp);
-    every variant must give the oracle's bits, also for batches that leave a warp partly empty."""
-    os.environ["PCL_POLAR_S"] = str(S)
+@pytest.mark.parametrize("NL", [1, 0])
+def test_compiled_code_length_variants(NL):
+    """PCL_POLAR_NL=0 forces the kernel that reads log2 N and G at run time; 1 (default) lets
+    the library pick the variants compiled for N = 1024 / 256.  Both must give the oracle's
+    bits, also for batches that leave a warp partly empty and for code lengths without a
+    compiled variant."""
+    S = NL
+    os.environ["PCL_POLAR_NL"] = str(NL)
     try:
-        for N, K, L, F in ((512, 256, 8, 1003), (1024, 700, 4, 517), (128, 64, 2, 999), (2048, 1024, 8, 130)):
+        for N, K, L, F in ((512, 256, 8, 1003), (1024, 700, 4, 517), (128, 64, 2, 999), (2048, 1024, 8, 130),
+                           (1024, 512, 8, 1001), (1024, 849, 32, 203), (256, 128, 8, 999), (256, 128, 1, 1000),
+                           (1024, 512, 1, 777), (64, 30, 16, 500), (32, 20, 8, 300), (16, 9, 4, 300)):
             frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
             _, llr = _polar_frames(N, K, frozen, F, 0.5, N + L + S)
             ref = oracle.polar_scl(N, L, frozen, llr, nthreads=8)
@@ -375,9 +380,11 @@ def test_lanes_per_path_variants(S):
                 dec = P.SCLDecoder(N, K, list_size=L, frozen_bits=frozen, dtype=dt)
                 got = dec.decode_batch(llr)
                 bad = int((got != ref).any(axis=1).sum())
-                assert bad == 0 if dt == "float64" else bad <= 1, f"N={N} L={L} S={S} {dt}: {bad} frames differ"
+                assert bad == 0 if dt == "float64" else bad <= 1, f"N={N} L={L} NL={NL} {dt}: {bad} frames differ"
+                if NL and dt == "float32" and (N, L) in ((1024, 8), (1024, 32), (256, 8)):
+                    assert dec.launch_info()["compiled_code_length"]
     finally:
-        os.environ.pop("PCL_POLAR_S")
+        os.environ.pop("PCL_POLAR_NL")
 
 
 def test_large_codes():
