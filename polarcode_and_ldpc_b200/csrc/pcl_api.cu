@@ -152,9 +152,13 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
 // Kernel variants.  Generic: one frame per warp, every level in shared memory.  Fast: a lane
 // owns a path, 32 / LP frames per warp (polar_scl_fast.cuh); X(LP, log2 N, G) with log2 N = 0
 // for the run-time code length, else the code length and G compiled in as constants.
+#ifdef PCL_QUICK   // experiment builds (scripts/build_variants.py): headline kernels only
+#define PCL_POLAR_FAST_VARIANTS(X) X(8, 0, 0) X(8, 10, 5)
+#else
 #define PCL_POLAR_FAST_VARIANTS(X) \
     X(1, 0, 0) X(2, 0, 0) X(4, 0, 0) X(8, 0, 0) X(16, 0, 0) X(32, 0, 0) \
     X(1, 10, 5) X(8, 10, 5) X(32, 10, 5) X(1, 8, 2) X(8, 8, 2)
+#endif
 
 static bool polar_fast_variant_exists(int LP, int nl, int gl)
 {
@@ -173,12 +177,14 @@ static int polar_with_kernel(pcl_polar* h, Fn&& fn)
 #undef X
     } else {
         switch (h->LP) {
+#ifndef PCL_QUICK
             case 1: return fn(polar_scl_kernel<1, real>);
             case 2: return fn(polar_scl_kernel<2, real>);
             case 4: return fn(polar_scl_kernel<4, real>);
-            case 8: return fn(polar_scl_kernel<8, real>);
             case 16: return fn(polar_scl_kernel<16, real>);
             case 32: return fn(polar_scl_kernel<32, real>);
+#endif
+            case 8: return fn(polar_scl_kernel<8, real>);
         }
     }
     return fail(PCL_EUNSUPPORTED, "no kernel for list size %d", h->L);
@@ -449,6 +455,9 @@ static int ldpc_with_kernel(pcl_ldpc* h, Fn&& fn)
         return fn(ldpc_decode_kernel<real, 1, 8, 0>);
     }
     if (h->regular6) return fn(ldpc_decode_kernel<real, 0, 6, 1>);
+#ifdef PCL_QUICK
+    return fail(PCL_EUNSUPPORTED, "experiment build");
+#endif
     if (h->dmax <= 8) return fn(ldpc_decode_kernel<real, 0, 8, 0>);
     if (h->dmax <= 16) return fn(ldpc_decode_kernel<real, 0, 16, 0>);
     return fn(ldpc_decode_kernel<real, 0, 32, 0>);

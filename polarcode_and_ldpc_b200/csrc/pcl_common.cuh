@@ -29,6 +29,9 @@ __device__ __forceinline__ unsigned char* pcl_dyn_smem()
 }
 #endif
 
+struct pcl_true { static constexpr bool value = true; };
+struct pcl_false { static constexpr bool value = false; };
+
 // ---- bit-field helpers -------------------------------------------------------
 PCL_DEVICE uint32_t pcl_bfe(uint32_t w, int pos, int len)
 {

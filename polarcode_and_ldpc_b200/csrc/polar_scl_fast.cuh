@@ -132,6 +132,26 @@ PCL_DEVICE void pcl_load_quad<double>(const double* ptr, double* v)
     v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
 }
 
+// channel LLRs are read once per visit of level 2 and never written: streaming loads keep them
+// from displacing the scratch levels in L2
+template <typename real>
+PCL_DEVICE void pcl_load_quad_stream(const real* ptr, real* v);
+template <>
+PCL_DEVICE void pcl_load_quad_stream<float>(const float* ptr, float* v)
+{
+#if defined(PCL_EMU) || !defined(PCL_STREAM_LLR)
+    pcl_load_quad<float>(ptr, v);
+#else
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(ptr));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+#endif
+}
+template <>
+PCL_DEVICE void pcl_load_quad_stream<double>(const double* ptr, double* v)
+{
+    pcl_load_quad<double>(ptr, v);
+}
+
 template <typename real>
 PCL_DEVICE void pcl_store_quad(real* ptr, const real* v);
 template <>
@@ -172,6 +192,33 @@ PCL_DEVICE void pcl_load_pair<double>(const double* ptr, double& a, double& b)
 // LP = 1 (SC) never prunes and needs none.
 PCL_HOST_DEVICE constexpr int pcl_fast_frame_bytes(int LP) { return LP == 1 ? 0 : ((LP * 28 + 15) / 16) * 16; }
 
+// Scratch levels in global memory: optional L2-only accesses (-DPCL_SCRATCH_CG)
+template <bool GLOBAL, typename real>
+PCL_DEVICE void pcl_ldq(const real* ptr, real* v)
+{
+#if !defined(PCL_EMU) && defined(PCL_SCRATCH_CG)
+    if (GLOBAL && sizeof(real) == 4) {
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(ptr));
+        v[0] = (real)q.x; v[1] = (real)q.y; v[2] = (real)q.z; v[3] = (real)q.w;
+        return;
+    }
+#endif
+    pcl_load_quad<real>(ptr, v);
+}
+template <bool GLOBAL, typename real>
+PCL_DEVICE void pcl_stq(real* ptr, const real* v)
+{
+#if !defined(PCL_EMU) && defined(PCL_SCRATCH_CG)
+    if (GLOBAL && sizeof(real) == 4) {
+        float4 q;
+        q.x = (float)v[0]; q.y = (float)v[1]; q.z = (float)v[2]; q.w = (float)v[3];
+        __stcg(reinterpret_cast<float4*>(ptr), q);
+        return;
+    }
+#endif
+    pcl_store_quad<real>(ptr, v);
+}
+
 // One quad (4 consecutive elements of a path) of a butterfly stage.
 template <bool BIT, typename real>
 PCL_DEVICE void pcl_quad_op(real* out, const real* a, const real* b, uint32_t nbits)
@@ -188,22 +235,22 @@ PCL_DEVICE void pcl_quad_op(real* out, const real* a, const real* b, uint32_t nb
 // Two batches of two quads: the loads of the next batch are in flight while the current one is
 // computed.  The partial-sum bits of 8 consecutive quads sit in one word: `bsrc` (stride 32
 // words, levels of >= 32 elements) or the register field `smf` (16 elements).
-template <bool BIT, typename real>
+template <bool BIT, bool GS, bool GD, typename real>
 PCL_DEVICE void pcl_level_vec(real* dst, const real* src, int nq, const uint32_t* bsrc, uint32_t smf)
 {
     real a[2][4], b[2][4], a2[2][4], b2[2][4];
     uint32_t wb = smf;
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-        pcl_load_quad<real>(src + u * 128, a[u]);
-        pcl_load_quad<real>(src + (u + nq) * 128, b[u]);
+        pcl_ldq<GS, real>(src + u * 128, a[u]);
+        pcl_ldq<GS, real>(src + (u + nq) * 128, b[u]);
     }
 #pragma unroll 2
     for (int i = 0; i < nq; i += 4) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            pcl_load_quad<real>(src + (i + 2 + u) * 128, a2[u]);
-            pcl_load_quad<real>(src + (i + 2 + u + nq) * 128, b2[u]);
+            pcl_ldq<GS, real>(src + (i + 2 + u) * 128, a2[u]);
+            pcl_ldq<GS, real>(src + (i + 2 + u + nq) * 128, b2[u]);
         }
         if (BIT && bsrc != nullptr && (i & 7) == 0) wb = bsrc[(i >> 3) * 32];
         const uint32_t w4 = wb >> (4 * (i & 7));
@@ -211,20 +258,20 @@ PCL_DEVICE void pcl_level_vec(real* dst, const real* src, int nq, const uint32_t
         for (int u = 0; u < 2; u++) {
             real out[4];
             pcl_quad_op<BIT, real>(out, a[u], b[u], w4 >> (4 * u));
-            pcl_store_quad<real>(dst + (i + u) * 128, out);
+            pcl_stq<GD, real>(dst + (i + u) * 128, out);
         }
         if (i + 4 < nq) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                pcl_load_quad<real>(src + (i + 4 + u) * 128, a[u]);
-                pcl_load_quad<real>(src + (i + 4 + u + nq) * 128, b[u]);
+                pcl_ldq<GS, real>(src + (i + 4 + u) * 128, a[u]);
+                pcl_ldq<GS, real>(src + (i + 4 + u + nq) * 128, b[u]);
             }
         }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             real out[4];
             pcl_quad_op<BIT, real>(out, a2[u], b2[u], w4 >> (8 + 4 * u));
-            pcl_store_quad<real>(dst + (i + 2 + u) * 128, out);
+            pcl_stq<GD, real>(dst + (i + 2 + u) * 128, out);
         }
     }
 }
@@ -233,7 +280,7 @@ PCL_DEVICE void pcl_level_vec(real* dst, const real* src, int nq, const uint32_t
 // level 2 = elements 4 i4 + r; element k comes from the 4 channel values at 4 br(k), and
 // br(4 i4 + r) = br(i4) + br2(r) * sz / 4: four sequential streams of 16-byte loads, one
 // 16-byte store.  b1 = left array of level 1, b2 = left array of level 2 (nullptr: `smf`).
-template <bool BIT1, bool BIT, typename real>
+template <bool BIT1, bool BIT, bool GD, typename real>
 PCL_DEVICE void pcl_level2_vec(real* dst, const real* y, int n, const uint32_t* b1, const uint32_t* b2, uint32_t smf)
 {
     const int sz = 1 << (n - 2);
@@ -243,7 +290,7 @@ PCL_DEVICE void pcl_level2_vec(real* dst, const real* y, int n, const uint32_t* 
         const int i4 = (int)(__brev((unsigned)tl) >> (36 - n));    // (n-4)-bit reversal
         real yv[4][4];
 #pragma unroll
-        for (int mm = 0; mm < 4; mm++) pcl_load_quad<real>(y + 4 * (tl + mm * nq), yv[mm]);
+        for (int mm = 0; mm < 4; mm++) pcl_load_quad_stream<real>(y + 4 * (tl + mm * nq), yv[mm]);
         const int k4 = 4 * i4;
         uint32_t n1 = 0, n2 = 0, n0 = 0;
         if (BIT1) {
@@ -265,14 +312,14 @@ PCL_DEVICE void pcl_level2_vec(real* dst, const real* y, int n, const uint32_t* 
             }
             out[r] = BIT ? pcl_fast<real>::gs(a, b, n0 << (31 - r)) : pcl_math<real>::f(a, b);
         }
-        pcl_store_quad<real>(dst + i4 * 128, out);
+        pcl_stq<GD, real>(dst + i4 * 128, out);
     }
 }
 
 // LP = list slots per frame (power of two); a warp decodes FPW = 32 / LP frames side by side.
 // NL = log2 N as a compile-time constant (0: read it from the layout), GL = G for that NL.
 #ifndef PCL_POLAR_MINB
-#define PCL_POLAR_MINB 5      // resident 128-thread blocks per SM the register allocation aims for (96 regs)
+#define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for (80 regs)
 #endif
 template <int LP, typename real, int NL, int GL>
 __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3) polar_scl_fast_kernel(PolarParams<real> P)
@@ -336,19 +383,23 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                 const uint32_t* b1src = bw + cbase + (ptrB & (LP - 1));     // left array of level 1
                 if (start <= 2) {
                     if (act) {
-                        real* dst = ((2 <= G) ? gl : sl) + 4 * lane;
                         const int bit1 = (i0 >> (n - 1)) & 1;
                         const int bit = (i0 >> (n - 2)) & 1;
                         const uint32_t* b2src = (2 <= nb) ? bw + 32 * ((N >> 5) - (N >> 6)) + cbase + ((ptrB >> PB) & (LP - 1))
                                                           : nullptr;
                         const uint32_t smf = small;                         // n == 6: level 2 has 16 elements
-                        if (bit1) {
-                            if (bit) pcl_level2_vec<true, true, real>(dst, y, n, b1src, b2src, smf);
-                            else pcl_level2_vec<true, false, real>(dst, y, n, b1src, b2src, smf);
-                        } else {
-                            if (bit) pcl_level2_vec<false, true, real>(dst, y, n, b1src, b2src, smf);
-                            else pcl_level2_vec<false, false, real>(dst, y, n, b1src, b2src, smf);
-                        }
+                        auto run2 = [&](auto gd, real* dst) {
+                            constexpr bool GD = decltype(gd)::value;
+                            if (bit1) {
+                                if (bit) pcl_level2_vec<true, true, GD, real>(dst, y, n, b1src, b2src, smf);
+                                else pcl_level2_vec<true, false, GD, real>(dst, y, n, b1src, b2src, smf);
+                            } else {
+                                if (bit) pcl_level2_vec<false, true, GD, real>(dst, y, n, b1src, b2src, smf);
+                                else pcl_level2_vec<false, false, GD, real>(dst, y, n, b1src, b2src, smf);
+                            }
+                        };
+                        if (2 <= G) run2(pcl_true(), gl + 4 * lane);
+                        else run2(pcl_false(), sl + 4 * lane);
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << PB)) | ((uint32_t)p << PB);
                     }
                 }
@@ -367,30 +418,39 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                         if (d <= G) {
                             const real* src = gl + 32 * ((N >> 1) - (N >> (d - 2))) + soff;
                             real* dst = gl + 32 * ((N >> 1) - (N >> (d - 1))) + doff;
-                            if (bit) pcl_level_vec<true, real>(dst, src, nq, bsrc, smf);
-                            else pcl_level_vec<false, real>(dst, src, nq, bsrc, smf);
+                            if (bit) pcl_level_vec<true, true, true, real>(dst, src, nq, bsrc, smf);
+                            else pcl_level_vec<false, true, true, real>(dst, src, nq, bsrc, smf);
                         } else if (d - 1 <= G) {
                             const real* src = gl + 32 * ((N >> 1) - (N >> (d - 2))) + soff;
                             real* dst = sl + 32 * ((N >> G) - (N >> (d - 1))) + doff;
-                            if (bit) pcl_level_vec<true, real>(dst, src, nq, bsrc, smf);
-                            else pcl_level_vec<false, real>(dst, src, nq, bsrc, smf);
+                            if (bit) pcl_level_vec<true, true, false, real>(dst, src, nq, bsrc, smf);
+                            else pcl_level_vec<false, true, false, real>(dst, src, nq, bsrc, smf);
                         } else {
                             const real* src = sl + 32 * ((N >> G) - (N >> (d - 2))) + soff;
                             real* dst = sl + 32 * ((N >> G) - (N >> (d - 1))) + doff;
-                            if (bit) pcl_level_vec<true, real>(dst, src, nq, bsrc, smf);
-                            else pcl_level_vec<false, real>(dst, src, nq, bsrc, smf);
+                            if (bit) pcl_level_vec<true, false, false, real>(dst, src, nq, bsrc, smf);
+                            else pcl_level_vec<false, false, false, real>(dst, src, nq, bsrc, smf);
                         }
                         ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
                     }
                 }
                 if (act) {                        // level n-3 from the four quads of level n-4
                     const int q = (ptrL >> ((n - 5) * PB)) & (LP - 1);
-                    const real* src = ((n - 4 <= G) ? gl + 32 * ((N >> 1) - 32) : sl + 32 * ((N >> G) - 32)) + 4 * (cbase + q);
                     real qa[2][4], qb[2][4];
+                    if (n - 4 <= G) {
+                        const real* src = gl + 32 * ((N >> 1) - 32) + 4 * (cbase + q);
 #pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        pcl_load_quad<real>(src + u * 128, qa[u]);
-                        pcl_load_quad<real>(src + (u + 2) * 128, qb[u]);
+                        for (int u = 0; u < 2; u++) {
+                            pcl_ldq<true, real>(src + u * 128, qa[u]);
+                            pcl_ldq<true, real>(src + (u + 2) * 128, qb[u]);
+                        }
+                    } else {
+                        const real* src = sl + 32 * ((N >> G) - 32) + 4 * (cbase + q);
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            pcl_ldq<false, real>(src + u * 128, qa[u]);
+                            pcl_ldq<false, real>(src + (u + 2) * 128, qb[u]);
+                        }
                     }
                     if (bit3) {
 #pragma unroll
