@@ -96,15 +96,19 @@ PCL_DEVICE void cn_bp_exact(double* msg, int d)
     }
 }
 
-// ---- check node, fp32 production rule (t and w = 1 - |t| side by side) ---------
-// MUFU budget per edge: ex2 + rcp on the way in, rcp + lg2 on the way out.
-//   u = exp(-|x|) = 2^(-|x| log2 e) (rel. err ~ |x| * 6e-8: enters the outgoing LLR additively)
-//   w = 1 - tanh(|x|/2) = 2u / (1 + u)   keeps full RELATIVE precision near |t| -> 1,
-//   t = (1 - u) / (1 + u)                keeps full ABSOLUTE precision near t -> 0.
-// Leave-one-out: p_i = prod t_j, q_i = 1 - prod (1 - w_j) (sums of positive terms, no
-// cancellation).  Output 2 atanh(p): q < 1/4 -> ln((2-q)/q); |p| < 1/8 -> odd series;
-// otherwise ln((1+|p|)/(1-|p|)).  Both clips of the reference (+-0.999999 on t and on the
-// product, decoder.py:82,88) become w >= 1e-6 and q >= 1e-6.
+// ---- check node, fp32 production rule (even / odd symmetric sums of u = exp(-|x|)) ----
+// tanh(|x|/2) = (1 - u) / (1 + u) with u = exp(-|x|), so for the other edges of a check
+//   prod t_j = (E - O) / (E + O),   prod (1 + u_j) = E + O,   prod (1 - u_j) = E - O,
+// E / O = the even / odd elementary symmetric sums of the u_j, and the outgoing message is
+//   2 atanh(prod t_j) = ln((1 + p) / (1 - p)) = ln(E / O).
+// E and O are sums of positive terms only: no cancellation anywhere, full relative precision
+// both for saturated messages (all u ~ 1e-6: O ~ sum u_j) and for weak ones (u ~ 1: E ~ O).
+// A factor (1 + u) maps (E, O) -> (E + u O, O + u E); the leave-one-out pair comes from a
+// prefix and a suffix pair: E = Ep Es + Op Os, O = Ep Os + Op Es.  Three MUFU ops per edge
+// (ex2 in; rcp, lg2 out).  The reference's clips (+-0.999999 on t and on the product,
+// decoder.py:82,88) become u >= (1 - 0.999999) / (1 + 0.999999) and E / O <= 1999999; an
+// absent edge (irregular codes) is u = 0, the identity factor; a degree-1 check gives
+// E / O = 1 / 0 -> clipped -> ln(1999999) = 14.5087, as the reference does.
 PCL_DEVICE float pcl_ex2(float x)
 {
 #ifdef PCL_EMU
@@ -136,57 +140,67 @@ PCL_DEVICE float pcl_rcp(float x)
 #endif
 }
 
-template <int DMAX>
+// VEC2: the check's DMAX messages start at an 8-byte boundary and all exist (regular codes):
+// 8-byte shared-memory accesses, conflict-free at a stride of 6 words.
+template <int DMAX, bool VEC2>
 PCL_DEVICE void cn_bp_f32(float* msg, int d)
 {
-    // magnitudes and signs travel separately: products of non-negative numbers only, the
-    // leave-one-out sign is an XOR of sign bits
-    float t[DMAX], w[DMAX];
-    uint32_t sg[DMAX];
+    const float UMIN = 5.00000250000125e-07f, RMAX = 1999999.0f;
+    float u[DMAX];
+    uint32_t xb[DMAX];
     uint32_t sall = 0;
+    if (VEC2) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j += 2) {
+            const float2 v = reinterpret_cast<const float2*>(msg)[j >> 1];
+            xb[j] = __float_as_uint(v.x);
+            xb[j + 1] = __float_as_uint(v.y);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) xb[j] = (j < d) ? __float_as_uint(msg[j]) : 0x7f800000u;   // +inf: u = 0
+    }
 #pragma unroll
     for (int j = 0; j < DMAX; j++) {
-        if (j < d) {
-            const float x = msg[j];
-            const float u = pcl_ex2(fabsf(x) * -1.4426950408889634f);   // exp(-|x|), rel. err ~ |x| * 6e-8
-            const float r = pcl_rcp(1.0f + u);
-            w[j] = fmaxf((u + u) * r, 1e-6f);                           // 1 - |t|, clipped
-            t[j] = fminf((1.0f - u) * r, 0.999999f);                    // |t|, clipped
-            sg[j] = __float_as_uint(x) & 0x80000000u;
-            sall ^= sg[j];
-        } else {
-            t[j] = 1.0f;
-            w[j] = 0.0f;
-            sg[j] = 0u;
-        }
+        const float ax = fabsf(__uint_as_float(xb[j]));
+        const float e = pcl_ex2(ax * -1.4426950408889634f);           // exp(-|x|), rel. err ~ |x| * 6e-8
+        u[j] = (VEC2 || j < d) ? fmaxf(e, UMIN) : 0.0f;
+        sall ^= xb[j];
     }
-    // suffix products, then a running prefix
-    float st[DMAX + 1], sq[DMAX + 1];
-    st[DMAX] = 1.0f;
-    sq[DMAX] = 0.0f;
+    // suffix pairs, then a running prefix pair
+    float se[DMAX + 1], so[DMAX + 1];
+    se[DMAX] = 1.0f;
+    so[DMAX] = 0.0f;
 #pragma unroll
-    for (int j = DMAX - 1; j >= 0; j--) {
-        st[j] = st[j + 1] * t[j];
-        sq[j] = fmaf(-sq[j + 1], w[j], sq[j + 1] + w[j]);      // 1 - (1-a)(1-b)
+    for (int j = DMAX - 1; j >= 1; j--) {
+        se[j] = fmaf(u[j], so[j + 1], se[j + 1]);
+        so[j] = fmaf(u[j], se[j + 1], so[j + 1]);
     }
-    float pt = 1.0f, pq = 0.0f;
+    float pe = 1.0f, po = 0.0f;
+    float out[DMAX];
 #pragma unroll
     for (int i = 0; i < DMAX; i++) {
-        if (i < d) {
-            const float ap = pt * st[i + 1];                    // |p_i|
-            float q = fmaf(-pq, sq[i + 1], pq + sq[i + 1]);     // 1 - |p_i| from the w side
-            q = fmaxf(q, 1e-6f);                                // |p| <= 0.999999
-            const bool near1 = q < 0.25f;
-            const float num = near1 ? 2.0f - q : 1.0f + ap;
-            const float den = near1 ? q : 1.0f - ap;
-            float mag = 0.6931471805599453f * pcl_lg2(num * pcl_rcp(den));
-            const float p2 = ap * ap;
-            const float ser = (ap + ap) * fmaf(p2, fmaf(p2, fmaf(p2, 0.14285715f, 0.2f), 0.33333334f), 1.0f);
-            if (ap < 0.125f) mag = ser;                         // q >= 0.875 there, never near1
-            msg[i] = __uint_as_float(__float_as_uint(mag) | (sall ^ sg[i]));
+        const float E = fmaf(po, so[i + 1], pe * se[i + 1]);
+        const float O = fmaf(po, se[i + 1], pe * so[i + 1]);
+        const float ratio = fminf(E * pcl_rcp(O), RMAX);
+        const float mag = 0.6931471805599453f * pcl_lg2(ratio);
+        out[i] = __uint_as_float(__float_as_uint(mag) | ((sall ^ xb[i]) & 0x80000000u));
+        const float npe = fmaf(u[i], po, pe);
+        po = fmaf(u[i], pe, po);
+        pe = npe;
+    }
+    if (VEC2) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j += 2) {
+            float2 v;
+            v.x = out[j];
+            v.y = out[j + 1];
+            reinterpret_cast<float2*>(msg)[j >> 1] = v;
         }
-        pt = pt * t[i];
-        pq = fmaf(-pq, w[i], pq + w[i]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++)
+            if (j < d) msg[j] = out[j];
     }
 }
 
@@ -273,7 +287,7 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
                     cn_ms<real>(msg + e0, d, P.norm);
                 } else {
                     if (sizeof(real) == 8) cn_bp_exact<DMAX>((double*)(msg + e0), d);
-                    else cn_bp_f32<DMAX>((float*)(msg + e0), d);
+                    else cn_bp_f32<DMAX, (REG != 0 && DMAX % 2 == 0)>((float*)(msg + e0), d);
                 }
             }
             __syncwarp();
