@@ -124,39 +124,31 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ inputs ------
-def make_inputs(w, torch, device, seed):
-    """Synthetic frames of the workload's shape, generated on the device (plumbing only):
-    random message -> encode -> BPSK + AWGN -> LLR = 2y/sigma^2 (reference: channel/awgn.py:47,75)."""
+_GEN_CACHE = {}
+
+
+def make_inputs(w, torch, device, seed, frame0=0):
+    """Synthetic frames of the workload's shape from the library's own on-device generator
+    (csrc/framegen.cuh: random message -> encode -> BPSK + AWGN -> LLR = 2y/sigma^2, reference
+    channel/awgn.py:47,75).  Returns (llr, reference bits the decoder output is compared with, code)."""
     import polarcode_and_ldpc_b200 as P
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
     F = w["frames"]
-    snr_lin = 10 ** (w["snr"] / 10.0)
-    sigma = float(np.sqrt(1.0 / (2.0 * snr_lin)))
     if w["kind"] == "polar":
-        N, K = w["N"], w["K"]
-        frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
-        info = np.setdiff1d(np.arange(N), frozen)
-        msg = torch.randint(0, 2, (F, K), generator=g, device=device, dtype=torch.uint8)
-        u = torch.zeros((F, N), dtype=torch.uint8, device=device)
-        u[:, torch.from_numpy(info).to(device)] = msg
-        stride = 1
-        while stride < N:                      # x = u F^{(x)n}  (reference: polar/utils.py:193-229)
-            v = u.view(F, N // (2 * stride), 2, stride)
-            v[:, :, 0, :] ^= v[:, :, 1, :]
-            stride *= 2
-        cw, ref, code = u, msg, dict(frozen=frozen)
-    else:
-        n = w["n"]
-        H = P.gallager_parity_check(n, 3, 6, 42)
-        G, infopos = P.generator_from_parity(H)
-        k = G.shape[0]
-        msg = torch.randint(0, 2, (F, k), generator=g, device=device, dtype=torch.uint8)
-        cw = (msg.float() @ torch.from_numpy(G).float().to(device)).remainder_(2).to(torch.uint8)
-        ref, code = cw, dict(H=H, k_true=k)
-    noise = torch.randn((F, cw.shape[1]), generator=g, device=device, dtype=torch.float32)
-    llr = ((1.0 - 2.0 * cw.float()) + sigma * noise) * (2.0 / sigma ** 2)
-    return llr.contiguous(), ref.contiguous(), code
+        key = ("polar", w["N"], w["K"])
+        if key not in _GEN_CACHE:
+            frozen = P.bhattacharyya_frozen_set(w["N"], w["K"], 2.0)
+            _GEN_CACHE[key] = (P.FrameGenerator.polar(w["N"], w["K"], frozen), dict(frozen=frozen))
+        gen, code = _GEN_CACHE[key]
+        llr, msg, _ = gen.generate(F, w["snr"], seed=seed, frame0=frame0, device=device, want_codeword=False)
+        return llr, msg, code
+    key = ("ldpc", w["n"])
+    if key not in _GEN_CACHE:
+        H = P.gallager_parity_check(w["n"], 3, 6, 42)
+        G, _ = P.generator_from_parity(H)
+        _GEN_CACHE[key] = (P.FrameGenerator.ldpc(G), dict(H=H, k_true=G.shape[0]))
+    gen, code = _GEN_CACHE[key]
+    llr, _, cw = gen.generate(F, w["snr"], seed=seed, frame0=frame0, device=device, want_message=False)
+    return llr, cw, code
 
 
 def make_decoder(w, code, dtype="float32"):
@@ -175,7 +167,7 @@ def run_gpu_workload(name, args, torch, dist, rank, world, device, with_e2e=True
     w = dict(WORKLOADS[name])
     if args.frames:
         w["frames"] = args.frames
-    llr, ref, code = make_inputs(w, torch, device, seed=1234 + rank)
+    llr, ref, code = make_inputs(w, torch, device, seed=1234, frame0=rank * w["frames"])
     dec = make_decoder(w, code)
     F = w["frames"]
     kbits = info_bits(w)

@@ -9,8 +9,9 @@ ends the sweep.  K = int(N * rate) as at :200.  The reference's sequential `max_
 
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 benchmarks/snr_sweep.py --frames 1000000
     python benchmarks/snr_sweep.py --frames 20000          # single GPU
-Frames are generated on the device (message -> encode -> BPSK + AWGN, same formulas as
-src/channel/awgn.py:47,75); per-rank seeds are recorded in the output.
+Frames are generated on the device by the library's generator (csrc/framegen.cuh: message ->
+encode -> BPSK + AWGN, same formulas as src/channel/awgn.py:47,75).  Frame f of a point is a
+function of (seed, point, f) only, so the counters do not depend on the number of ranks.
 """
 from __future__ import annotations
 
@@ -36,6 +37,7 @@ def main():
     ap.add_argument("--list-size", type=int, default=8)
     ap.add_argument("--snrs", default="-2,-1,0,1,2,3,4,5")
     ap.add_argument("--rates", default="0.50,0.67,0.75,0.83")
+    ap.add_argument("--seed", type=int, default=20240101)
     ap.add_argument("--output", default="results/snr_sweep.json")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -60,7 +62,7 @@ def main():
         dec = None
         for c0 in range(lo, hi, a.chunk):
             w["frames"] = min(a.chunk, hi - c0)
-            llr, ref, codeinfo = bench.make_inputs(w, torch, dev, seed=1000003 * rank + 7919 * pi + c0)
+            llr, ref, codeinfo = bench.make_inputs(w, torch, dev, seed=a.seed + 7919 * pi, frame0=c0)
             if dec is None:
                 if code == "polar":
                     dec = P.SCLDecoder(N, w["K"], list_size=a.list_size, frozen_bits=codeinfo["frozen"])
@@ -71,7 +73,7 @@ def main():
     torch.cuda.synchronize()
     ber, fer = counters.rates()
     if rank == 0:
-        out = {"frames_per_point": a.frames, "world_size": world, "seconds": time.time() - t0,
+        out = {"frames_per_point": a.frames, "world_size": world, "seed": a.seed, "seconds": time.time() - t0,
                "points": [{"code": c, "rate": r, "snr_db": s, "ber": float(ber[i]), "fer": float(fer[i]),
                            "counters": counters.t[i].tolist()} for i, (c, r, s) in enumerate(points)]}
         os.makedirs(os.path.dirname(a.output) or ".", exist_ok=True)

@@ -39,6 +39,7 @@ extern "C" {
 
 typedef struct pcl_polar pcl_polar_t;
 typedef struct pcl_ldpc pcl_ldpc_t;
+typedef struct pcl_gen pcl_gen_t;
 
 int pcl_version(void);
 const char* pcl_last_error(void);
@@ -99,6 +100,26 @@ int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t
                          int32_t* iters_host, void* stream);
 int pcl_ldpc_num_edges(const pcl_ldpc_t* h);
 int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, int* smem_bytes);
+
+/*
+ * On-device frame generation for BER / FER sweeps: the per-frame pipeline of the reference's
+ * callers (benchmarks/benchmark_scl.py:95-103, test_snr_curves.py:121-130):
+ *   message = randint(0, 2, K); codeword = encoder.encode(message); llr = AWGNChannel(snr).transmit(codeword)
+ * with PolarEncoder.encode (src/polar/encoder.py:52-95, transform src/polar/utils.py:193-229),
+ * LDPCEncoder.encode (src/ldpc/encoder.py:76-93, c = m G mod 2) and AWGNChannel.transmit
+ * (src/channel/awgn.py:47,75,88).  Random bits and noise come from Philox4x32-10 keyed by
+ * `seed` and addressed by the GLOBAL frame index frame0 + f, so a frame's content does not
+ * depend on how a sweep is sharded.  frozen_mask[N] as in pcl_polar_create; G_dense [k][n]
+ * bytes, row-major.  Outputs (device): msg_dev [F][K] bytes (optional), cw_dev [F][N] bytes
+ * (optional), llr_dev [F][N] in `dtype`.
+ */
+int pcl_gen_polar_create(pcl_gen_t** out, int N, int K, const uint8_t* frozen_mask);
+int pcl_gen_ldpc_create(pcl_gen_t** out, int n, int k, const uint8_t* G_dense);
+void pcl_gen_destroy(pcl_gen_t* h);
+int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, double snr_db,
+                   int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev, void* stream);
+/* One Philox4x32-10 block evaluated on the host from the same source (known-answer tests). */
+void pcl_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /*
  * np.sum(message != decoded) loops of the callers (benchmarks/test_snr_curves.py:

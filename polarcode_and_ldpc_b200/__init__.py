@@ -14,5 +14,6 @@ from .ldpc.encoder import LDPCEncoder                      # noqa: F401
 from .ldpc.construction import gallager_parity_check, mackay_parity_check, generator_from_parity  # noqa: F401
 from .channel.awgn import AWGNChannel                      # noqa: F401
 from .sweep import ErrorCounters, count_errors, shard_range  # noqa: F401
+from .framegen import FrameGenerator                        # noqa: F401
 
 __version__ = "0.1.0"

@@ -8,6 +8,7 @@
 #include "pcl_common.cuh"
 #include "polar_scl.cuh"
 #include "polar_scl_fast.cuh"
+#include "framegen.cuh"
 #include "ldpc_bp.cuh"
 #include "../../include/pcl.h"
 
@@ -698,6 +699,105 @@ extern "C" int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t
     for (int s = 0; s < PCL_NSTAGE; s++) CUDA_TRY(cudaStreamSynchronize(h->st[s]));
     return PCL_OK;
 #endif
+}
+
+// ============================================================ frame generator ===
+struct pcl_gen {
+    int kind = 0, N = 0, K = 0, NW = 0;
+    uint32_t* d_info_words = nullptr;
+    uint16_t* d_info_rank = nullptr;
+    uint32_t* d_G = nullptr;
+};
+
+extern "C" void pcl_gen_destroy(pcl_gen_t* h)
+{
+    if (!h) return;
+    cudaFree(h->d_info_words);
+    cudaFree(h->d_info_rank);
+    cudaFree(h->d_G);
+    delete h;
+}
+
+extern "C" int pcl_gen_polar_create(pcl_gen_t** out, int N, int K, const uint8_t* frozen_mask)
+{
+    if (!out || !frozen_mask) return fail(PCL_EINVAL, "null argument");
+    if (N <= 0 || (N & (N - 1)) != 0 || N > 65536) return fail(PCL_EINVAL, "N must be a power of 2 (<= 65536)");
+    if (!(K > 0 && K < N)) return fail(PCL_EINVAL, "K must be in (0, N)");
+    const int NW = (N + 31) / 32;
+    std::vector<uint32_t> iw(NW, 0);
+    std::vector<uint16_t> rank(NW, 0);
+    int cnt = 0;
+    for (int w = 0; w < NW; w++) {
+        rank[w] = (uint16_t)cnt;
+        for (int b = 0; b < 32 && 32 * w + b < N; b++)
+            if (!frozen_mask[32 * w + b]) { iw[w] |= 1u << b; cnt++; }
+    }
+    if (cnt != K) return fail(PCL_EINVAL, "frozen mask leaves %d info positions, K=%d", cnt, K);
+    pcl_gen* h = new pcl_gen();
+    h->kind = 0; h->N = N; h->K = K; h->NW = NW;
+    if (cudaMalloc((void**)&h->d_info_words, NW * 4) != cudaSuccess ||
+        cudaMalloc((void**)&h->d_info_rank, NW * 2) != cudaSuccess ||
+        cudaMemcpy(h->d_info_words, iw.data(), NW * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->d_info_rank, rank.data(), NW * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+        pcl_gen_destroy(h);
+        return fail(PCL_ECUDA, "cudaMalloc / cudaMemcpy failed (generator tables)");
+    }
+    *out = h;
+    return PCL_OK;
+}
+
+extern "C" int pcl_gen_ldpc_create(pcl_gen_t** out, int n, int k, const uint8_t* G_dense)
+{
+    if (!out || !G_dense) return fail(PCL_EINVAL, "null argument");
+    if (n <= 0 || k <= 0 || k > n || n > 65536) return fail(PCL_EINVAL, "bad generator shape");
+    const int NW = (n + 31) / 32;
+    std::vector<uint32_t> g((size_t)k * NW, 0);
+    for (int r = 0; r < k; r++)
+        for (int c = 0; c < n; c++)
+            if (G_dense[(size_t)r * n + c] & 1) g[(size_t)r * NW + (c >> 5)] |= 1u << (c & 31);
+    pcl_gen* h = new pcl_gen();
+    h->kind = 1; h->N = n; h->K = k; h->NW = NW;
+    if (cudaMalloc((void**)&h->d_G, g.size() * 4) != cudaSuccess ||
+        cudaMemcpy(h->d_G, g.data(), g.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        pcl_gen_destroy(h);
+        return fail(PCL_ECUDA, "cudaMalloc / cudaMemcpy failed (generator matrix)");
+    }
+    *out = h;
+    return PCL_OK;
+}
+
+extern "C" int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, double snr_db,
+                              int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev, void* stream)
+{
+    if (!h || F < 0 || frame0 < 0) return fail(PCL_EINVAL, "bad handle, F or frame0");
+    if (dtype != PCL_F32 && dtype != PCL_F64) return fail(PCL_EINVAL, "bad dtype");
+    if (F == 0) return PCL_OK;
+    if (!llr_dev) return fail(PCL_EINVAL, "null buffer");
+    GenParams P;
+    P.kind = h->kind; P.N = h->N; P.K = h->K; P.NW = h->NW;
+    P.info_words = h->d_info_words; P.info_rank = h->d_info_rank; P.G = h->d_G;
+    P.F = F; P.frame0 = frame0;
+    P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
+    // src/channel/awgn.py:27-32: sigma = sqrt(1 / (2 snr_linear)); :75: LLR = 2 y / sigma^2
+    const double snr_lin = pow(10.0, snr_db / 10.0);
+    P.sigma64 = sqrt(1.0 / (2.0 * snr_lin));
+    P.scale64 = 2.0 / (P.sigma64 * P.sigma64);
+    P.sigma = (float)P.sigma64; P.scale = (float)P.scale64;
+    P.f64 = dtype == PCL_F64;
+    P.msg = msg_dev; P.cw = cw_dev; P.llr = llr_dev;
+    const int wpb = 4;
+    const int grid = (int)std::min<int64_t>((F + wpb - 1) / wpb, 148 * 16);
+    const int smem = wpb * h->NW * 4;
+    PCL_LAUNCH(framegen_kernel, grid, wpb * 32, smem, stream, P);
+    CUDA_TRY(cudaGetLastError());
+    return PCL_OK;
+}
+
+// Philox4x32-10 block for known-answer tests (host evaluation of the device function's source)
+extern "C" void pcl_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    const pcl_philox4 r = pcl_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
 // ============================================================ error counters ===

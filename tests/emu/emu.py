@@ -106,3 +106,39 @@ def ldpc_decode(H, llr, mode="bp", max_iter=50, normalization=1.0, early_stop=Tr
     L_.pcl_ldpc_destroy(h)
     out = (bits.astype(np.int64), iters)
     return out + (total,) if want_total else out
+
+
+def gen_frames(kind, N, K, table, F, snr_db, seed=0, frame0=0, dtype="f32"):
+    """csrc/framegen.cuh through the emulator: (llr[F, N], msg[F, K], cw[F, N]).
+    table = frozen_bits (polar) or G[k, n] (ldpc)."""
+    L_ = lib()
+    L_.pcl_gen_frames.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double,
+                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L_.simt_set_reverse(0)
+    h = ctypes.c_void_p()
+    if kind == "polar":
+        fm = np.zeros(N, dtype=np.uint8)
+        fm[np.asarray(table, dtype=np.int64)] = 1
+        rc = L_.pcl_gen_polar_create(ctypes.byref(h), N, K, _vp(fm))
+    else:
+        G8 = np.ascontiguousarray(np.asarray(table) % 2, dtype=np.uint8)
+        rc = L_.pcl_gen_ldpc_create(ctypes.byref(h), N, K, _vp(G8))
+    if rc:
+        raise RuntimeError(f"gen create rc={rc}: {L_.pcl_last_error().decode()}")
+    rt = np.float64 if dtype == "f64" else np.float32
+    llr = np.zeros((F, N), dtype=rt)
+    msg = np.full((F, K), 7, dtype=np.uint8)
+    cw = np.full((F, N), 7, dtype=np.uint8)
+    rc = L_.pcl_gen_frames(h, F, frame0, seed, float(snr_db), 1 if dtype == "f64" else 0, _vp(msg), _vp(cw), _vp(llr), None)
+    if rc:
+        raise RuntimeError(f"gen rc={rc}: {L_.pcl_last_error().decode()}")
+    L_.pcl_gen_destroy.argtypes = [ctypes.c_void_p]
+    L_.pcl_gen_destroy(h)
+    return llr, msg, cw
+
+
+def philox(counter, key):
+    L_ = lib()
+    c, k, out = np.asarray(counter, dtype=np.uint32), np.asarray(key, dtype=np.uint32), np.zeros(4, dtype=np.uint32)
+    L_.pcl_philox4x32_10_host(_vp(c), _vp(k), _vp(out))
+    return out

@@ -247,6 +247,7 @@ inline int __all_sync(unsigned m, int pred) {
     return (b & full) == full;
 }
 
+inline void sincospif(float x, float* s, float* c) { *s = sinf(3.14159265358979323846f * x); *c = cosf(3.14159265358979323846f * x); }
 inline int __ffs(int v) { return v ? __builtin_ffs(v) : 0; }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
