@@ -15,5 +15,6 @@ from .ldpc.construction import gallager_parity_check, mackay_parity_check, gener
 from .channel.awgn import AWGNChannel                      # noqa: F401
 from .sweep import ErrorCounters, count_errors, shard_range  # noqa: F401
 from .framegen import FrameGenerator                        # noqa: F401
+from .simulate import make_ldpc_code, make_polar_code, simulate_point  # noqa: F401
 
 __version__ = "0.1.0"
