@@ -118,6 +118,16 @@ int pcl_gen_ldpc_create(pcl_gen_t** out, int n, int k, const uint8_t* G_dense);
 void pcl_gen_destroy(pcl_gen_t* h);
 int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, double snr_db,
                    int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev, void* stream);
+/* Same with a channel choice: PCL_CH_AWGN (param = SNR in dB), PCL_CH_RAYLEIGH (param = average
+ * SNR in dB; RayleighFadingChannel.transmit, src/channel/fading.py:26-52: y = |h| s + n,
+ * LLR = 2 y |h| / sigma^2) or PCL_CH_BSC (param = crossover probability in (0, 1);
+ * BSCChannel.transmit, src/channel/bsc.py:24-39, delivered as LLR = +-ln((1 - p) / p)). */
+#define PCL_CH_AWGN 0
+#define PCL_CH_RAYLEIGH 1
+#define PCL_CH_BSC 2
+int pcl_gen_frames_channel(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, int channel,
+                           double param, int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev,
+                           void* stream);
 /* One Philox4x32-10 block evaluated on the host from the same source (known-answer tests). */
 void pcl_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

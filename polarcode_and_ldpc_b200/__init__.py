@@ -12,7 +12,7 @@ from .polar.construction import bhattacharyya_frozen_set   # noqa: F401
 from .ldpc.decoder import BPDecoder, MSDecoder             # noqa: F401
 from .ldpc.encoder import LDPCEncoder                      # noqa: F401
 from .ldpc.construction import gallager_parity_check, mackay_parity_check, generator_from_parity  # noqa: F401
-from .channel.awgn import AWGNChannel                      # noqa: F401
+from .channel import AWGNChannel, BSCChannel, RayleighFadingChannel  # noqa: F401
 from .sweep import ErrorCounters, count_errors, shard_range  # noqa: F401
 from .framegen import FrameGenerator                        # noqa: F401
 from .simulate import make_ldpc_code, make_polar_code, simulate_point  # noqa: F401

@@ -58,6 +58,7 @@ def lib() -> ctypes.CDLL:
     L.pcl_gen_destroy.argtypes = [vp]
     L.pcl_gen_destroy.restype = None
     L.pcl_gen_frames.argtypes = [vp, i64, i64, ctypes.c_uint64, ctypes.c_double, i32, vp, vp, vp, vp]
+    L.pcl_gen_frames_channel.argtypes = [vp, i64, i64, ctypes.c_uint64, i32, ctypes.c_double, i32, vp, vp, vp, vp]
     L.pcl_philox4x32_10_host.argtypes = [vp, vp, vp]
     L.pcl_philox4x32_10_host.restype = None
     _lib = L
@@ -70,7 +71,7 @@ EXPORTS = [
     "pcl_polar_lp", "pcl_polar_launch_info",
     "pcl_ldpc_create", "pcl_ldpc_destroy", "pcl_ldpc_decode_batch", "pcl_ldpc_decode_host",
     "pcl_ldpc_num_edges", "pcl_ldpc_launch_info", "pcl_count_errors",
-    "pcl_gen_polar_create", "pcl_gen_ldpc_create", "pcl_gen_destroy", "pcl_gen_frames", "pcl_philox4x32_10_host",
+    "pcl_gen_polar_create", "pcl_gen_ldpc_create", "pcl_gen_destroy", "pcl_gen_frames", "pcl_gen_frames_channel", "pcl_philox4x32_10_host",
 ]
 
 

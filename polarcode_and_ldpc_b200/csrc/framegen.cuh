@@ -12,7 +12,12 @@
 //   * LDPC encode c = m G mod 2 (src/ldpc/encoder.py:88-90) as the XOR of the bit-packed rows
 //     of G selected by the message bits;
 //   * BPSK 0 -> +1, 1 -> -1, y = s + sigma z, LLR = 2 y / sigma^2 (src/channel/awgn.py:47,75,88),
-//     z from Box-Muller on two Philox words.
+//     z from Box-Muller on two Philox words;
+//   * Rayleigh fading with perfect channel knowledge (src/channel/fading.py:26-52): y = |h| s +
+//     sigma z, LLR = 2 y |h| / sigma^2, |h|^2 = hr^2 + hi^2 with hr, hi ~ N(0, 1/2), i.e. |h|^2 is
+//     exponential with mean 1: |h| = sqrt(-ln u);
+//   * binary symmetric channel (src/channel/bsc.py:24-39): the bit flips with probability p; the
+//     decoders are fed LLR = +-ln((1 - p) / p) of the received bit.
 // The host numpy path (channel/awgn.py: transmit_batch) stays the one that reproduces the
 // reference's np.random stream exactly; this one removes the host RNG and the PCIe copy from
 // sweeps.
@@ -39,7 +44,12 @@ PCL_HOST_DEVICE pcl_philox4 pcl_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     return o;
 }
 
-enum { PCL_STREAM_MSG = 0, PCL_STREAM_NOISE = 1 };
+enum { PCL_STREAM_MSG = 0, PCL_STREAM_NOISE = 1, PCL_STREAM_FADE = 2 };
+#ifndef PCL_CH_AWGN          // include/pcl.h
+#define PCL_CH_AWGN 0
+#define PCL_CH_RAYLEIGH 1
+#define PCL_CH_BSC 2
+#endif
 
 struct GenParams {
     int kind;                     // 0 polar, 1 LDPC
@@ -51,6 +61,8 @@ struct GenParams {
     uint32_t seed_lo, seed_hi;
     float sigma, scale;           // noise std and 2 / sigma^2
     double scale64, sigma64;
+    int channel;                  // PCL_CH_*
+    float bsc_p, bsc_llr;         // BSC: crossover probability and ln((1 - p) / p)
     int f64;                      // LLR output type
     uint8_t* msg;                 // [F][K] message bytes (optional)
     uint8_t* cw;                  // [F][N] codeword bytes (optional)
@@ -127,20 +139,34 @@ __global__ void __launch_bounds__(128) framegen_kernel(GenParams P)
             }
             __syncwarp();
         }
-        // BPSK + AWGN -> LLR; element i = 32 t + lane, four elements per Philox call
+        // channel -> LLR; element i = 32 t + lane, four elements per Philox call
         for (int t0 = 0; 32 * t0 < N; t0 += 4) {
-            const pcl_philox4 r = pcl_philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32),
-                                                    (uint32_t)((t0 >> 2) * 32 + lane), PCL_STREAM_NOISE, P.seed_lo, P.seed_hi);
-            float z[4];
+            const uint32_t blk = (uint32_t)((t0 >> 2) * 32 + lane);
+            const pcl_philox4 r = pcl_philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), blk, PCL_STREAM_NOISE,
+                                                    P.seed_lo, P.seed_hi);
+            float z[4], hm[4];
+            if (P.channel == PCL_CH_BSC) {
+                z[0] = (float)r.x; z[1] = (float)r.y; z[2] = (float)r.z; z[3] = (float)r.w;
+            } else {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t a = h ? r.z : r.x, b = h ? r.w : r.y;
-                const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) 2^-32
-                const float rad = sqrtf(-2.0f * logf(u1));
-                float sn, cs;
-                sincospif((float)b * 4.656612873077393e-10f, &sn, &cs);                             // 2 pi b 2^-32
-                z[2 * h] = rad * cs;
-                z[2 * h + 1] = rad * sn;
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t a = h ? r.z : r.x, b = h ? r.w : r.y;
+                    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (a + 0.5) 2^-32
+                    const float rad = sqrtf(-2.0f * logf(u1));
+                    float sn, cs;
+                    sincospif((float)b * 4.656612873077393e-10f, &sn, &cs);                             // 2 pi b 2^-32
+                    z[2 * h] = rad * cs;
+                    z[2 * h + 1] = rad * sn;
+                }
+            }
+            hm[0] = hm[1] = hm[2] = hm[3] = 1.0f;
+            if (P.channel == PCL_CH_RAYLEIGH) {
+                const pcl_philox4 g = pcl_philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), blk, PCL_STREAM_FADE,
+                                                        P.seed_lo, P.seed_hi);
+                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    hm[q] = sqrtf(-logf(fmaf((float)gw[q], 2.3283064365386963e-10f, 1.1641532182693481e-10f)));
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -150,8 +176,16 @@ __global__ void __launch_bounds__(128) framegen_kernel(GenParams P)
                     const uint32_t bit = (U[t] >> lane) & 1u;
                     if (P.cw != nullptr) P.cw[f * N + i] = (uint8_t)bit;
                     const float s = bit ? -1.0f : 1.0f;
-                    if (P.f64) ((double*)P.llr)[f * N + i] = ((double)s + P.sigma64 * (double)z[q]) * P.scale64;
-                    else ((float*)P.llr)[f * N + i] = fmaf(P.sigma, z[q], s) * P.scale;
+                    if (P.channel == PCL_CH_BSC) {
+                        const bool flip = z[q] * 2.3283064365386963e-10f < P.bsc_p;      // uniform [0, 1)
+                        const float v = (flip ? -s : s) * P.bsc_llr;
+                        if (P.f64) ((double*)P.llr)[f * N + i] = (double)v;
+                        else ((float*)P.llr)[f * N + i] = v;
+                    } else if (P.f64) {
+                        ((double*)P.llr)[f * N + i] = ((double)hm[q] * (double)s + P.sigma64 * (double)z[q]) * (double)hm[q] * P.scale64;
+                    } else {
+                        ((float*)P.llr)[f * N + i] = fmaf(P.sigma, z[q], hm[q] * s) * hm[q] * P.scale;
+                    }
                 }
             }
         }

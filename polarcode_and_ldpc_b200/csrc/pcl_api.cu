@@ -766,11 +766,15 @@ extern "C" int pcl_gen_ldpc_create(pcl_gen_t** out, int n, int k, const uint8_t*
     return PCL_OK;
 }
 
-extern "C" int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, double snr_db,
-                              int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev, void* stream)
+extern "C" int pcl_gen_frames_channel(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, int channel,
+                                      double param, int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev,
+                                      void* stream)
 {
     if (!h || F < 0 || frame0 < 0) return fail(PCL_EINVAL, "bad handle, F or frame0");
     if (dtype != PCL_F32 && dtype != PCL_F64) return fail(PCL_EINVAL, "bad dtype");
+    if (channel < PCL_CH_AWGN || channel > PCL_CH_BSC) return fail(PCL_EINVAL, "bad channel");
+    if (channel == PCL_CH_BSC && !(param > 0.0 && param < 1.0))
+        return fail(PCL_EINVAL, "BSC crossover probability must be in (0, 1) to give finite LLRs");
     if (F == 0) return PCL_OK;
     if (!llr_dev) return fail(PCL_EINVAL, "null buffer");
     GenParams P;
@@ -778,11 +782,14 @@ extern "C" int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned 
     P.info_words = h->d_info_words; P.info_rank = h->d_info_rank; P.G = h->d_G;
     P.F = F; P.frame0 = frame0;
     P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32);
-    // src/channel/awgn.py:27-32: sigma = sqrt(1 / (2 snr_linear)); :75: LLR = 2 y / sigma^2
-    const double snr_lin = pow(10.0, snr_db / 10.0);
+    P.channel = channel;
+    // src/channel/awgn.py:27-32 (and fading.py:18-20): sigma = sqrt(1 / (2 snr_linear)); LLR = 2 y / sigma^2
+    const double snr_lin = pow(10.0, (channel == PCL_CH_BSC ? 0.0 : param) / 10.0);
     P.sigma64 = sqrt(1.0 / (2.0 * snr_lin));
     P.scale64 = 2.0 / (P.sigma64 * P.sigma64);
     P.sigma = (float)P.sigma64; P.scale = (float)P.scale64;
+    P.bsc_p = channel == PCL_CH_BSC ? (float)param : 0.0f;
+    P.bsc_llr = channel == PCL_CH_BSC ? (float)log((1.0 - param) / param) : 0.0f;
     P.f64 = dtype == PCL_F64;
     P.msg = msg_dev; P.cw = cw_dev; P.llr = llr_dev;
     const int wpb = 4;
@@ -791,6 +798,12 @@ extern "C" int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned 
     PCL_LAUNCH(framegen_kernel, grid, wpb * 32, smem, stream, P);
     CUDA_TRY(cudaGetLastError());
     return PCL_OK;
+}
+
+extern "C" int pcl_gen_frames(pcl_gen_t* h, int64_t F, int64_t frame0, unsigned long long seed, double snr_db,
+                              int dtype, uint8_t* msg_dev, uint8_t* cw_dev, void* llr_dev, void* stream)
+{
+    return pcl_gen_frames_channel(h, F, frame0, seed, PCL_CH_AWGN, snr_db, dtype, msg_dev, cw_dev, llr_dev, stream);
 }
 
 // Philox4x32-10 block for known-answer tests (host evaluation of the device function's source)

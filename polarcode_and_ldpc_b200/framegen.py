@@ -49,8 +49,13 @@ class FrameGenerator:
         _native.check(_native.lib().pcl_gen_ldpc_create(ctypes.byref(h), n, k, ctypes.c_void_p(G.ctypes.data)))
         return cls(h, n, k, "ldpc")
 
+    CHANNELS = {"awgn": 0, "rayleigh": 1, "bsc": 2}
+
     def generate(self, F: int, snr_db: float, seed: int = 0, frame0: int = 0, dtype="float32",
-                 device=None, want_codeword: bool = True, want_message: bool = True):
+                 device=None, want_codeword: bool = True, want_message: bool = True, channel: str = "awgn"):
+        """channel: "awgn" (AWGNChannel(snr_db)), "rayleigh" (RayleighFadingChannel(snr_db), perfect
+        channel knowledge) or "bsc" (BSCChannel(crossover_prob=snr_db): the second argument is then
+        the crossover probability and the LLRs are +-ln((1 - p) / p))."""
         torch = _native.require_cuda()
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         code = _native.dtype_code(dtype)
@@ -60,8 +65,8 @@ class FrameGenerator:
         cw = torch.empty((F, self.N), dtype=torch.uint8, device=device) if want_codeword else None
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream().cuda_stream
-            _native.check(_native.lib().pcl_gen_frames(
-                self._h, F, frame0, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), float(snr_db), code,
+            _native.check(_native.lib().pcl_gen_frames_channel(
+                self._h, F, frame0, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self.CHANNELS[channel], float(snr_db), code,
                 ctypes.c_void_p(msg.data_ptr()) if msg is not None and F else None,
                 ctypes.c_void_p(cw.data_ptr()) if cw is not None and F else None,
                 ctypes.c_void_p(llr.data_ptr()) if F else None, ctypes.c_void_p(stream)))

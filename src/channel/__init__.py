@@ -1,1 +1,1 @@
-from polarcode_and_ldpc_b200.channel.awgn import AWGNChannel  # noqa: F401
+from polarcode_and_ldpc_b200.channel import AWGNChannel, BSCChannel, RayleighFadingChannel  # noqa: F401

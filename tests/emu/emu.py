@@ -108,12 +108,13 @@ def ldpc_decode(H, llr, mode="bp", max_iter=50, normalization=1.0, early_stop=Tr
     return out + (total,) if want_total else out
 
 
-def gen_frames(kind, N, K, table, F, snr_db, seed=0, frame0=0, dtype="f32"):
+def gen_frames(kind, N, K, table, F, snr_db, seed=0, frame0=0, dtype="f32", channel=0):
     """csrc/framegen.cuh through the emulator: (llr[F, N], msg[F, K], cw[F, N]).
     table = frozen_bits (polar) or G[k, n] (ldpc)."""
     L_ = lib()
-    L_.pcl_gen_frames.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double,
-                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L_.pcl_gen_frames_channel.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]
     L_.simt_set_reverse(0)
     h = ctypes.c_void_p()
     if kind == "polar":
@@ -129,7 +130,8 @@ def gen_frames(kind, N, K, table, F, snr_db, seed=0, frame0=0, dtype="f32"):
     llr = np.zeros((F, N), dtype=rt)
     msg = np.full((F, K), 7, dtype=np.uint8)
     cw = np.full((F, N), 7, dtype=np.uint8)
-    rc = L_.pcl_gen_frames(h, F, frame0, seed, float(snr_db), 1 if dtype == "f64" else 0, _vp(msg), _vp(cw), _vp(llr), None)
+    rc = L_.pcl_gen_frames_channel(h, F, frame0, seed, channel, float(snr_db), 1 if dtype == "f64" else 0, _vp(msg),
+                                   _vp(cw), _vp(llr), None)
     if rc:
         raise RuntimeError(f"gen rc={rc}: {L_.pcl_last_error().decode()}")
     L_.pcl_gen_destroy.argtypes = [ctypes.c_void_p]

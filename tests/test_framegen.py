@@ -76,6 +76,50 @@ def test_emu_frames_do_not_depend_on_sharding():
     assert not np.array_equal(full[1], other[1])
 
 
+def _check_other_channels(gen_fn):
+    """Rayleigh: s LLR sigma^2 / 2 = h^2 + sigma h z with h^2 ~ Exp(1) (fading.py:38-47);
+    BSC: flips with probability p, LLR = +-ln((1 - p) / p) (bsc.py:36-38)."""
+    llr, _, cw = gen_fn(channel="rayleigh", param=3.0)
+    sig = P.RayleighFadingChannel(3.0).noise_std
+    v = (1.0 - 2.0 * cw) * llr.astype(np.float64) * sig ** 2 / 2.0
+    n = v.size
+    assert abs(v.mean() - 1.0) < 5.0 * np.sqrt((1.0 + sig ** 2) / n)              # E h^2 = 1
+    assert abs(v.var() - (1.0 + sig ** 2)) < 0.05                                # Var h^2 + sigma^2 E h^2
+    ref = P.RayleighFadingChannel(3.0)
+    np.random.seed(0)
+    host = (1.0 - 2.0 * cw) * ref.transmit_batch(cw) * sig ** 2 / 2.0
+    assert abs(np.median(v) - np.median(host)) < 0.02 and abs((v < 0).mean() - (host < 0).mean()) < 0.01
+    p = 0.07
+    llr, _, cw = gen_fn(channel="bsc", param=p)
+    mag = np.log((1 - p) / p)
+    np.testing.assert_allclose(np.abs(llr), mag, rtol=1e-6)
+    flips = (llr < 0).astype(np.int64) != cw
+    assert abs(flips.mean() - p) < 5.0 * np.sqrt(p * (1 - p) / flips.size)
+
+
+def test_emu_rayleigh_and_bsc_channels():
+    fz = P.bhattacharyya_frozen_set(256, 128, 2.0)
+
+    def gen_fn(channel, param):
+        return emu.gen_frames("polar", 256, 128, fz, 96, param, seed=3, channel={"rayleigh": 1, "bsc": 2}[channel])
+    _check_other_channels(gen_fn)
+
+
+@pytest.mark.gpu
+def test_gpu_rayleigh_and_bsc_channels():
+    fz = P.bhattacharyya_frozen_set(1024, 512, 2.0)
+    gen = P.FrameGenerator.polar(1024, 512, fz)
+
+    def gen_fn(channel, param):
+        llr, msg, cw = gen.generate(512, param, seed=3, channel=channel)
+        return llr.cpu().numpy(), msg.cpu().numpy(), cw.cpu().numpy().astype(np.int64)
+    _check_other_channels(gen_fn)
+    # decoders take the LLRs of either channel: BSC(0.03) through SCL-8 at rate 1/2 decodes clean
+    llr, msg, _ = gen.generate(2048, 0.03, seed=9, channel="bsc")
+    c = P.count_errors(P.SCLDecoder(1024, 512, 8, fz).decode_batch(llr), msg)
+    assert c[1].item() < 20
+
+
 @pytest.mark.gpu
 def test_gpu_framegen_matches_host_encoders_and_statistics():
     import torch
