@@ -32,7 +32,8 @@ struct LdpcLayout {
     int m, n, E;
     int max_iter, early_stop;
     int nhw;                    // hard-decision words = ceil(n / 32)
-    int off_msg, off_llr, off_hard, warp_bytes;
+    int off_msg, off_llr, off_hard, off_ctl, warp_bytes;
+    int coop;                   // 1: the whole block decodes one frame (large codes), 0: one warp per frame
 };
 
 template <typename real>
@@ -227,6 +228,72 @@ PCL_DEVICE void cn_ms(real* msg, int d, real norm)
     }
 }
 
+// Regular codes: all DMAX messages of the check exist and start at an 8-byte boundary.  The two
+// smallest magnitudes come from a branch-free min / max ladder; edge i takes the second one iff
+// its own magnitude is the smallest (equal minima make the two the same number, so comparing
+// values needs no index); sign = product of the other signs as an XOR of sign bits.  A zero
+// among the other inputs makes the minimum 0, which is what np.sign(0) = 0 gives (:270-285).
+template <typename real> struct ldpc_bits;
+template <> struct ldpc_bits<float> {
+    typedef uint32_t u;
+    static PCL_DEVICE u of(float x) { return __float_as_uint(x); }
+    static PCL_DEVICE float to(u b) { return __uint_as_float(b); }
+    static PCL_DEVICE u sign() { return 0x80000000u; }
+};
+template <> struct ldpc_bits<double> {
+    typedef unsigned long long u;
+    static PCL_DEVICE u of(double x) { return (u)__double_as_longlong(x); }
+    static PCL_DEVICE double to(u b) { return __longlong_as_double((long long)b); }
+    static PCL_DEVICE u sign() { return 0x8000000000000000ull; }
+};
+
+template <typename real, int DMAX>
+PCL_DEVICE void cn_ms_reg(real* msg, real norm)
+{
+    typedef typename ldpc_bits<real>::u bits_t;
+    real x[DMAX], a[DMAX];
+    if (sizeof(real) == 4 && DMAX % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j += 2) {
+            const float2 v = reinterpret_cast<const float2*>(msg)[j >> 1];
+            x[j] = (real)v.x;
+            x[j + 1] = (real)v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) x[j] = msg[j];
+    }
+    bits_t sall = 0;
+    real m1 = pcl_math<real>::inf(), m2 = pcl_math<real>::inf();
+#pragma unroll
+    for (int j = 0; j < DMAX; j++) {
+        a[j] = fabs(x[j]);
+        // np.sign: a NaN-free input is negative iff x < 0 (-0.0 is not)
+        sall ^= (x[j] < (real)0) ? ldpc_bits<real>::sign() : (bits_t)0;
+        m2 = fmin(m2, fmax(m1, a[j]));
+        m1 = fmin(m1, a[j]);
+    }
+    real out[DMAX];
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+        const real mn = (a[i] > m1) ? m1 : m2;
+        const bits_t sg = sall ^ ((x[i] < (real)0) ? ldpc_bits<real>::sign() : (bits_t)0);
+        out[i] = ldpc_bits<real>::to(ldpc_bits<real>::of(mn * norm) ^ sg);       // (+-1 * min) * norm, :285
+    }
+    if (sizeof(real) == 4 && DMAX % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j += 2) {
+            float2 v;
+            v.x = (float)out[j];
+            v.y = (float)out[j + 1];
+            reinterpret_cast<float2*>(msg)[j >> 1] = v;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) msg[j] = out[j];
+    }
+}
+
 // numpy add.reduce association order (pairwise_sum) over gathered messages
 template <typename real>
 PCL_DEVICE real vn_sum_np(const real* msg, const uint16_t* ed, int d)
@@ -252,50 +319,68 @@ PCL_DEVICE real vn_sum_np(const real* msg, const uint16_t* ed, int d)
 // REG != 0: every check has degree DMAX and every variable degree 3 (the regular (3, DMAX)
 // Gallager codes of the benchmarks): degrees and edge offsets become compile-time constants,
 // no pointer-table loads and no per-edge degree predicates.
-template <typename real, int MODE, int DMAX, int REG>
+template <typename real, int MODE, int DMAX, int REG, int COOP>
 __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
 {
     const LdpcLayout& Y = P.lay;
     const int m = Y.m, n = Y.n, E = Y.E;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char* wsm = pcl_dyn_smem() + (size_t)warp * Y.warp_bytes;
+    // Large codes (a frame's messages take a big share of the SM's shared memory) are decoded by
+    // the whole block: `tid` of `T` threads strides over checks / variables and the passes are
+    // separated by block barriers; small codes keep one warp per frame and warp barriers.
+    constexpr bool coop = COOP != 0;
+    const int T = coop ? (int)blockDim.x : 32;
+    const int tid = coop ? (int)threadIdx.x : lane;
+    unsigned char* wsm = pcl_dyn_smem() + (coop ? (size_t)0 : (size_t)warp * Y.warp_bytes);
     real* msg = (real*)(wsm + Y.off_msg);
     real* sllr = (real*)(wsm + Y.off_llr);
     uint32_t* hard = (uint32_t*)(wsm + Y.off_hard);
+    unsigned long long* ctl = (unsigned long long*)(wsm + Y.off_ctl);   // coop: frame index, stop flag
+    auto sync = [&]() {
+        if (coop) __syncthreads();
+        else __syncwarp();
+    };
 
     for (;;) {
         unsigned long long fq = 0;
-        if (lane == 0) fq = atomicAdd(P.next, 1ull);
-        fq = pcl_shfl_u64(fq, 0);
+        if (coop) {
+            if (tid == 0) ctl[0] = atomicAdd(P.next, 1ull);
+            __syncthreads();
+            fq = ctl[0];
+        } else {
+            if (lane == 0) fq = atomicAdd(P.next, 1ull);
+            fq = pcl_shfl_u64(fq, 0);
+        }
         if ((int64_t)fq >= P.F) break;
         const int64_t f = (int64_t)fq;
 
         const real* ch = P.llr + f * n;
-        for (int v = lane; v < n; v += 32) sllr[v] = ch[v];
-        __syncwarp();
-        for (int e = lane; e < E; e += 32) msg[e] = sllr[P.col[e]];   // decoder.py:144-146
-        __syncwarp();
+        for (int v = tid; v < n; v += T) sllr[v] = ch[v];
+        sync();
+        for (int e = tid; e < E; e += T) msg[e] = sllr[P.col[e]];   // decoder.py:144-146
+        sync();
 
         int iters = Y.max_iter;                                       // :149
         for (int it = 0; it < Y.max_iter; it++) {
             // 1. check nodes (:152-168)
-            for (int c = lane; c < m; c += 32) {
+            for (int c = tid; c < m; c += T) {
                 const int e0 = REG ? c * DMAX : P.cptr[c];
                 const int d = REG ? DMAX : P.cptr[c + 1] - e0;
                 if (MODE == 1) {
-                    cn_ms<real>(msg + e0, d, P.norm);
+                    if (REG) cn_ms_reg<real, DMAX>(msg + e0, P.norm);
+                    else cn_ms<real>(msg + e0, d, P.norm);
                 } else {
                     if (sizeof(real) == 8) cn_bp_exact<DMAX>((double*)(msg + e0), d);
                     else cn_bp_f32<DMAX, (REG != 0 && DMAX % 2 == 0)>((float*)(msg + e0), d);
                 }
             }
-            __syncwarp();
+            sync();
             // 2. variable nodes (:173-188) + 3. hard decision (:191)
             // (hard decisions are only materialised when something reads them: the syndrome test
             // or the output after the last iteration)
             const bool want_hard = Y.early_stop || it == Y.max_iter - 1;
-            for (int vb = 0; vb < n; vb += 32) {
+            for (int vb = coop ? warp * 32 : 0; vb < n; vb += T) {
                 const int v = vb + lane;
                 bool bit = false;
                 if (v < n) {
@@ -335,11 +420,11 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
                     if (lane == 0) hard[vb >> 5] = bal;
                 }
             }
-            __syncwarp();
+            sync();
             // 4. syndrome early stop (:194-198)
             if (Y.early_stop) {
                 bool bad = false;
-                for (int c = lane; c < m; c += 32) {
+                for (int c = tid; c < m; c += T) {
                     const int e0 = REG ? c * DMAX : P.cptr[c], e1 = REG ? e0 + DMAX : P.cptr[c + 1];
                     unsigned par = 0;
                     for (int e = e0; e < e1; e++) {
@@ -348,12 +433,20 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
                     }
                     bad |= (par & 1u) != 0;
                 }
-                if (!__any_sync(PCL_FULL_MASK, bad)) { iters = it + 1; break; }
+                bool any_bad = __any_sync(PCL_FULL_MASK, bad);
+                if (coop) {
+                    if (tid == 0) ctl[1] = 0ull;
+                    __syncthreads();
+                    if (any_bad && lane == 0) ctl[1] = 1ull;
+                    __syncthreads();
+                    any_bad = ctl[1] != 0ull;
+                }
+                if (!any_bad) { iters = it + 1; break; }
             }
         }
         uint8_t* out = P.bits + f * n;
-        for (int v = lane; v < n; v += 32) out[v] = (uint8_t)((hard[v >> 5] >> (v & 31)) & 1u);
-        if (P.iters != nullptr && lane == 0) P.iters[f] = iters;
-        __syncwarp();
+        for (int v = tid; v < n; v += T) out[v] = (uint8_t)((hard[v >> 5] >> (v & 31)) & 1u);
+        if (P.iters != nullptr && tid == 0) P.iters[f] = iters;
+        sync();
     }
 }

@@ -448,20 +448,27 @@ struct pcl_ldpc {
 #endif
 };
 
-template <typename real, typename Fn>
-static int ldpc_with_kernel(pcl_ldpc* h, Fn&& fn)
+template <typename real, int COOP, typename Fn>
+static int ldpc_with_kernel_c(pcl_ldpc* h, Fn&& fn)
 {
     if (h->mode == PCL_LDPC_MS) {
-        if (h->regular6) return fn(ldpc_decode_kernel<real, 1, 6, 1>);
-        return fn(ldpc_decode_kernel<real, 1, 8, 0>);
+        if (h->regular6) return fn(ldpc_decode_kernel<real, 1, 6, 1, COOP>);
+        return fn(ldpc_decode_kernel<real, 1, 8, 0, COOP>);
     }
-    if (h->regular6) return fn(ldpc_decode_kernel<real, 0, 6, 1>);
+    if (h->regular6) return fn(ldpc_decode_kernel<real, 0, 6, 1, COOP>);
 #ifdef PCL_QUICK
     return fail(PCL_EUNSUPPORTED, "experiment build");
 #endif
-    if (h->dmax <= 8) return fn(ldpc_decode_kernel<real, 0, 8, 0>);
-    if (h->dmax <= 16) return fn(ldpc_decode_kernel<real, 0, 16, 0>);
-    return fn(ldpc_decode_kernel<real, 0, 32, 0>);
+    if (h->dmax <= 8) return fn(ldpc_decode_kernel<real, 0, 8, 0, COOP>);
+    if (h->dmax <= 16) return fn(ldpc_decode_kernel<real, 0, 16, 0, COOP>);
+    return fn(ldpc_decode_kernel<real, 0, 32, 0, COOP>);
+}
+
+template <typename real, typename Fn>
+static int ldpc_with_kernel(pcl_ldpc* h, Fn&& fn)
+{
+    if (h->lay.coop) return ldpc_with_kernel_c<real, 1>(h, fn);
+    return ldpc_with_kernel_c<real, 0>(h, fn);
 }
 
 template <typename real>
@@ -540,7 +547,8 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     int off = 0;
     Y.off_msg = off;  off += align_up(std::max(E, 1) * rsz, 8);
     Y.off_llr = off;  off += align_up(n * rsz, 8);
-    Y.off_hard = off; off += Y.nhw * 4;
+    Y.off_hard = off; off += align_up(Y.nhw * 4, 8);
+    Y.off_ctl = off;  off += 16;
     Y.warp_bytes = align_up(off, 16);
 
     DeviceInfo di;
@@ -558,7 +566,16 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
         h->wpb = best_w;
     }
     while (h->wpb > 1 && Y.warp_bytes * h->wpb > di.smem_per_block) h->wpb >>= 1;
-    h->smem_bytes = Y.warp_bytes * h->wpb;
+    // Large codes: with one warp per frame fewer than ~16 warps fit on an SM; let a block of 4
+    // warps decode one frame together instead (4 x the resident warps, a quarter of the latency).
+    {
+        const int resident = (di.smem_per_sm / (Y.warp_bytes * h->wpb + 1024)) * h->wpb;
+        int coop = env_int("PCL_LDPC_COOP", -1);
+        if (coop < 0) coop = resident < 16 ? 1 : 0;
+        Y.coop = coop ? 1 : 0;
+        if (Y.coop) h->wpb = 4;
+    }
+    h->smem_bytes = Y.coop ? Y.warp_bytes : Y.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
         delete h;
         return fail(PCL_EUNSUPPORTED, "code too large: %d B of shared memory per frame", Y.warp_bytes);
@@ -634,7 +651,7 @@ static int ldpc_decode_impl(pcl_ldpc* h, const void* llr_dev, int64_t F, uint8_t
     P.F = F;
     P.norm = (real)h->norm;
     CUDA_TRY(cudaMemsetAsync(next, 0, 8, (cudaStream_t)stream));
-    int64_t need = (F + h->wpb - 1) / h->wpb;
+    int64_t need = h->lay.coop ? F : (F + h->wpb - 1) / h->wpb;
     int grid = (int)std::min<int64_t>(need, h->grid_max);
     h->last_grid = grid;
     int rc = ldpc_launch<real>(h, P, grid, stream);

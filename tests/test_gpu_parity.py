@@ -220,6 +220,29 @@ def test_ldpc_bulk_parity(mode):
     assert bad <= max(1, int(1e-4 * tot)), f"fp32 {mode}: {bad}/{tot} frames differ"
 
 
+@pytest.mark.parametrize("coop", ["0", "1"])
+def test_ldpc_warp_and_block_per_frame_agree(coop):
+    """PCL_LDPC_COOP forces one warp per frame (0) or one block per frame (1, what codes with
+    n >= 1008 get by default); both must reproduce the oracle."""
+    os.environ["PCL_LDPC_COOP"] = coop
+    try:
+        for n, mode in ((504, "bp"), (1008, "bp"), (1008, "ms")):
+            H = P.gallager_parity_check(n, 3, 6, 42)
+            np.random.seed(n)
+            llr = P.AWGNChannel(0.5).transmit_batch(np.zeros((777, n), dtype=int))
+            kw = dict(max_iter=20, early_stop=True)
+            if mode == "ms":
+                kw["normalization"] = 0.75
+            rb, ri = oracle.ldpc(H, llr, mode, nthreads=8, **kw)
+            cls = P.BPDecoder if mode == "bp" else P.MSDecoder
+            b, it = cls(H, dtype="float64", **kw).decode_batch(llr, return_iterations=True)
+            assert np.array_equal(b, rb) and np.array_equal(it, ri), (n, mode, coop)
+            b, it = cls(H, dtype="float32", **kw).decode_batch(llr, return_iterations=True)
+            assert int(((b != rb).any(axis=1) | (it != ri)).sum()) <= 1, (n, mode, coop)
+    finally:
+        os.environ.pop("PCL_LDPC_COOP")
+
+
 def test_ldpc_irregular_inrepo_H():
     """The in-repo mackay construction (rows of degree 0..13) used by throughput_test.py:285."""
     H = P.mackay_parity_check(504, 252, 3, 6, seed=42)

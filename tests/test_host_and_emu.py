@@ -160,3 +160,28 @@ def test_emu_ldpc_golden(golden_dir):
                 ref = g[name + "_total"][:3]
                 tol = 1e-9 if dt == "f64" else 1e-4
                 assert np.max(np.abs(tot - ref) / np.maximum(np.abs(ref), 1.0)) < tol
+
+
+def test_emu_ldpc_block_cooperative_mode():
+    """PCL_LDPC_COOP=1: the whole block decodes one frame (the mode large codes get); same bits
+    and iteration counts as one warp per frame and as the oracle, BP and Min-Sum, early stop on/off."""
+    rng = np.random.default_rng(0)
+    H = P.gallager_parity_check(96, 3, 6, 42)
+    llr = rng.normal(1.0, 2.2, size=(5, 96))
+    try:
+        for mode in ("bp", "ms"):
+            for es in (True, False):
+                rb, ri = oracle.ldpc(H, llr, mode, max_iter=8, normalization=0.75, early_stop=es)
+                for coop in ("0", "1"):
+                    os.environ["PCL_LDPC_COOP"] = coop
+                    for dt in ("f64", "f32"):
+                        b, it, _ = emu.ldpc_decode(H, llr, mode, 8, 0.75, es, dt, want_total=True)
+                        assert np.array_equal(b, rb) and np.array_equal(it, ri), (mode, es, coop, dt)
+        Hm = P.mackay_parity_check(120, 60, 3, 6, seed=42)
+        llr = rng.normal(1, 2, size=(3, 120))
+        rb, ri = oracle.ldpc(Hm, llr, "bp", max_iter=5)
+        os.environ["PCL_LDPC_COOP"] = "1"
+        b, it = emu.ldpc_decode(Hm, llr, "bp", 5)[:2]
+        assert np.array_equal(b, rb) and np.array_equal(it, ri)
+    finally:
+        os.environ.pop("PCL_LDPC_COOP", None)
