@@ -84,6 +84,11 @@ template <> struct pcl_fast<double> {
     static PCL_DEVICE double g(double a, double b, uint32_t bit) { return bit ? b - a : b + a; }
 };
 
+PCL_DEVICE double pcl_shfl_f64(double v, int src)
+{
+    return __longlong_as_double((long long)pcl_shfl_u64((uint64_t)__double_as_longlong(v), src));
+}
+
 template <typename real>
 PCL_DEVICE real pcl_shfl_real(real v, int src);
 template <>
@@ -318,6 +323,12 @@ PCL_DEVICE void pcl_level2_vec(real* dst, const real* y, int n, const uint32_t* 
 
 // LP = list slots per frame (power of two); a warp decodes FPW = 32 / LP frames side by side.
 // NL = log2 N as a compile-time constant (0: read it from the layout), GL = G for that NL.
+#ifndef PCL_PRUNE_SHORTCUT
+#define PCL_PRUNE_SHORTCUT 1
+#endif
+#ifndef PCL_PRUNE_QUICK
+#define PCL_PRUNE_QUICK 1
+#endif
 #ifndef PCL_POLAR_MINB
 #define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for (80 regs)
 #endif
@@ -547,61 +558,104 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
                         ka = pcl_prune_key<NC>(base, ida);
                         kb = pcl_prune_key<NC>(base - (double)ax, ida ^ LP);
                     }
+                    bool in_place = false;        // every survivor is its own parent's likely bit, same slot
+                    if (!EXACT && PCL_PRUNE_QUICK && nact >= L) {
+                        // Reliable bit on a full list (the common case): the likely keys are still in
+                        // slot order and every unlikely key lies below the last of them, so the ranks
+                        // are the slots themselves -- two shuffled compares instead of the ranking.
+                        const double ka_prev = pcl_shfl_f64(ka, p == 0 ? lane : lane - 1);
+                        const double ka_last = pcl_shfl_f64(ka, cbase + ns - 1);
+                        in_place = __all_sync(PCL_FULL_MASK, p >= ns || ((p == 0 || ka < ka_prev) && kb < ka_last));
+                    }
+                    if (!in_place) {
                     double2 kv;
                     kv.x = ka;
                     kv.y = kb;
                     *reinterpret_cast<double2*>(cm + 2 * p) = kv;
                     __syncwarp();
+                    if (EXACT || !PCL_PRUNE_SHORTCUT) {
 #pragma unroll
-                    for (int jj = 0; jj < NC; jj += 2) {
-                        const double2 kp = *reinterpret_cast<const double2*>(cm + jj);   // 16-byte aligned
-                        if (EXACT) {
-                            // position jj holds candidate (bit 0, path jj/2), jj + 1 (bit 1, path jj/2)
-                            const int q = jj >> 1;
-                            ra += (kp.x > ka) || (kp.x == ka && q < p);
-                            ra += (kp.y > ka);
-                            rb += (kp.x > kb) || (kp.x == kb);
-                            rb += (kp.y > kb) || (kp.y == kb && q < p);
+                        for (int jj = 0; jj < NC; jj += 2) {
+                            const double2 kp = *reinterpret_cast<const double2*>(cm + jj);   // 16-byte aligned
+                            if (EXACT) {
+                                // position jj holds candidate (bit 0, path jj/2), jj + 1 (bit 1, path jj/2)
+                                const int q = jj >> 1;
+                                ra += (kp.x > ka) || (kp.x == ka && q < p);
+                                ra += (kp.y > ka);
+                                rb += (kp.x > kb) || (kp.x == kb);
+                                rb += (kp.y > kb) || (kp.y == kb && q < p);
+                            } else {
+                                pcl_rank_acc(ra, kp.x, ka);
+                                pcl_rank_acc(rb, kp.x, kb);
+                                pcl_rank_acc(ra, kp.y, ka);
+                                pcl_rank_acc(rb, kp.y, kb);
+                            }
+                        }
+                    } else {
+                        // Ranks against the LP likely keys first.  An unlikely candidate with ns likely
+                        // keys above it is pruned, and if that holds for all of them (reliable bit: |x|
+                        // exceeds the spread of the list) no unlikely key can sit above a surviving
+                        // likely one either: the ranks among the likely keys are final and the second
+                        // half of the comparisons is skipped.  If the likely keys are moreover still in
+                        // slot order, every path simply continues in place: no scatter, no shuffles.
+#pragma unroll
+                        for (int q = 0; q < LP; q++) {
+                            const double kq = cm[2 * q];
+                            pcl_rank_acc(ra, kq, ka);
+                            pcl_rank_acc(rb, kq, kb);
+                        }
+                        if (__all_sync(PCL_FULL_MASK, rb >= ns)) {
+                            rb = NC;
+                            in_place = __all_sync(PCL_FULL_MASK, p >= ns || ra == p);
                         } else {
-                            pcl_rank_acc(ra, kp.x, ka);
-                            pcl_rank_acc(rb, kp.x, kb);
-                            pcl_rank_acc(ra, kp.y, ka);
-                            pcl_rank_acc(rb, kp.y, kb);
+#pragma unroll
+                            for (int q = 0; q < LP; q++) {
+                                const double kq = cm[2 * q + 1];
+                                pcl_rank_acc(ra, kq, ka);
+                                pcl_rank_acc(rb, kq, kb);
+                            }
                         }
                     }
-                    if (EXACT) {
-                        if (ra < ns) { sel[ra] = p; newpm[ra] = ka; }
-                        if (rb < ns) { sel[rb] = LP + p; newpm[rb] = kb; }
-                    } else {
-                        if (ra < ns) newpm[ra] = ka;
-                        if (rb < ns) newpm[rb] = kb;
-                    }
-                    __syncwarp();
-                    act = (p < ns) && valid;
-                    pm = DEAD;
-                    if (p < ns) {
-                        pm = newpm[p];
-                        const int c = EXACT ? sel[p] : (int)(__double_as_longlong(pm) & (NC - 1));
-                        parent = c & (LP - 1);
-                        u = (uint32_t)(c >> PB);
                     }
                     nact = ns;
-                    // a survivor takes over its parent's pointer words and live registers
-                    const int srcl = cbase | parent;
-                    ptrL = __shfl_sync(PCL_FULL_MASK, ptrL, srcl);
-                    ptrB = __shfl_sync(PCL_FULL_MASK, ptrB, srcl);
-                    small = __shfl_sync(PCL_FULL_MASK, small, srcl);
-                    if (j < 4) {
+                    if (in_place) {
+                        act = (p < ns) && valid;
+                        pm = (p < ns) ? ka : DEAD;
+                        u = hard ? 1u : 0u;
+                    } else {
+                        if (EXACT) {
+                            if (ra < ns) { sel[ra] = p; newpm[ra] = ka; }
+                            if (rb < ns) { sel[rb] = LP + p; newpm[rb] = kb; }
+                        } else {
+                            if (ra < ns) newpm[ra] = ka;
+                            if (rb < ns) newpm[rb] = kb;
+                        }
+                        __syncwarp();
+                        act = (p < ns) && valid;
+                        pm = DEAD;
+                        if (p < ns) {
+                            pm = newpm[p];
+                            const int c = EXACT ? sel[p] : (int)(__double_as_longlong(pm) & (NC - 1));
+                            parent = c & (LP - 1);
+                            u = (uint32_t)(c >> PB);
+                        }
+                        // a survivor takes over its parent's pointer words and live registers
+                        const int srcl = cbase | parent;
+                        ptrL = __shfl_sync(PCL_FULL_MASK, ptrL, srcl);
+                        ptrB = __shfl_sync(PCL_FULL_MASK, ptrB, srcl);
+                        small = __shfl_sync(PCL_FULL_MASK, small, srcl);
+                        if (j < 4) {
 #pragma unroll
-                        for (int t = 0; t < 8; t++) R3[t] = pcl_shfl_real<real>(R3[t], srcl);
-                    }
-                    if ((j & 3) < 2) {
+                            for (int t = 0; t < 8; t++) R3[t] = pcl_shfl_real<real>(R3[t], srcl);
+                        }
+                        if ((j & 3) < 2) {
 #pragma unroll
-                        for (int t = 0; t < 4; t++) R2[t] = pcl_shfl_real<real>(R2[t], srcl);
-                    }
-                    if ((j & 1) == 0) {
-                        R1[0] = pcl_shfl_real<real>(R1[0], srcl);
-                        R1[1] = pcl_shfl_real<real>(R1[1], srcl);
+                            for (int t = 0; t < 4; t++) R2[t] = pcl_shfl_real<real>(R2[t], srcl);
+                        }
+                        if ((j & 1) == 0) {
+                            R1[0] = pcl_shfl_real<real>(R1[0], srcl);
+                            R1[1] = pcl_shfl_real<real>(R1[1], srcl);
+                        }
                     }
                 }
                 if (P.dbg_leaf != nullptr && valid) {
