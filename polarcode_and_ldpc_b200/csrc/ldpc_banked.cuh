@@ -1,0 +1,144 @@
+// ldpc_banked.cuh -- flooding BP / Min-Sum for regular (3, DC) codes, fp32, with a
+// shared-memory layout in which NEITHER pass has bank conflicts.
+//
+// Same schedule and arithmetic as ldpc_bp.cuh (read that header first); what changes is where
+// an edge message lives.  ncu on the check-major layout (profiles/r01l): the shared-memory pipe
+// is the top limiter (83 %), 43 % of its wavefronts being bank conflicts of the variable-node
+// gather / scatter through `vperm` (random banks, ~2.6-way).  Here:
+//   * a check sits at (round R, lane l); its k-th message is word 32 (DC R + k) + l: a check
+//     round reads / writes DC rows of 32 consecutive words -- conflict free, no tables;
+//   * a variable sits at position pi = 32 r + lane; its three messages are fetched by three
+//     instructions, and the host chooses (a) the lane l of every check, (b) the round r of every
+//     variable, (c) which of a variable's edges each of the three instructions takes, such that
+//     the 32 words one instruction touches lie in 32 different banks (bank = l).  (a), (b) come
+//     from a short annealing run at handle creation (a round's 96 edges must hit every bank
+//     exactly 3 times), (c) from recolouring; the few edges that cannot be placed cost one extra
+//     wavefront each (3 of 1512 for the n = 504 code).
+// Hard decisions, the channel LLRs and the syndrome test live in position space; `varof` /
+// `posof` translate at frame load and store.  The variable sum adds its three messages in
+// instruction order, not in ascending check order (fp32 build only; the fp64 validation build
+// keeps ldpc_bp.cuh and the reference's order).
+#pragma once
+#include "ldpc_bp.cuh"
+
+template <int MODE, int DC, int COOP>
+__global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
+{
+    const LdpcLayout& Y = P.lay;
+    const int n = Y.n, nR = Y.nR, NP = Y.NP, NS = Y.NS;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    constexpr bool coop = COOP != 0;
+    const int T = coop ? (int)blockDim.x : 32;
+    const int tid = coop ? (int)threadIdx.x : lane;
+    const int w0 = coop ? warp : 0, wstep = coop ? (int)(blockDim.x >> 5) : 1;
+    unsigned char* wsm = pcl_dyn_smem() + (coop ? (size_t)0 : (size_t)warp * Y.warp_bytes);
+    float* msg = (float*)(wsm + Y.off_msg);
+    float* sllr = (float*)(wsm + Y.off_llr);
+    uint32_t* hard = (uint32_t*)(wsm + Y.off_hard);
+    unsigned long long* ctl = (unsigned long long*)(wsm + Y.off_ctl);
+    auto sync = [&]() {
+        if (coop) __syncthreads();
+        else __syncwarp();
+    };
+
+    for (;;) {
+        unsigned long long fq = 0;
+        if (coop) {
+            if (tid == 0) ctl[0] = atomicAdd(P.next, 1ull);
+            __syncthreads();
+            fq = ctl[0];
+        } else {
+            if (lane == 0) fq = atomicAdd(P.next, 1ull);
+            fq = pcl_shfl_u64(fq, 0);
+        }
+        if ((int64_t)fq >= P.F) break;
+        const int64_t f = (int64_t)fq;
+
+        const float* ch = P.llr + f * n;
+        for (int pi = tid; pi < NP; pi += T) {
+            const int v = P.varof[pi];
+            sllr[pi] = (v != 0xffff) ? ch[v] : 0.0f;
+        }
+        sync();
+        for (int s = tid; s < NS; s += T) {                            // decoder.py:144-146
+            const int cp = P.cpos[s];
+            msg[s] = (cp != 0xffff) ? sllr[cp] : 0.0f;
+        }
+        sync();
+
+        int iters = Y.max_iter;
+        for (int it = 0; it < Y.max_iter; it++) {
+            // 1. check nodes: round R, lane = the check's bank (an empty seat computes on zeros)
+            for (int R = w0; R < nR; R += wstep) {
+                float* base = msg + 32 * DC * R + lane;
+                float out[DC];
+                if (MODE == 1) {
+                    float x[DC];
+#pragma unroll
+                    for (int k = 0; k < DC; k++) x[k] = base[32 * k];
+                    cn_ms_core<float, DC>(x, out, P.norm);
+                } else {
+                    uint32_t xb[DC];
+#pragma unroll
+                    for (int k = 0; k < DC; k++) xb[k] = __float_as_uint(base[32 * k]);
+                    cn_bp_core<DC, true>(xb, out, DC);
+                }
+#pragma unroll
+                for (int k = 0; k < DC; k++) base[32 * k] = out[k];
+            }
+            sync();
+            // 2. variable nodes + 3. hard decision, in position space
+            const bool want_hard = Y.early_stop || it == Y.max_iter - 1;
+            for (int vb = 32 * w0; vb < NP; vb += 32 * wstep) {
+                const int pi = vb + lane;
+                const unsigned long long pk = P.bpack[pi];
+                bool bit = false;
+                if ((pk >> 48) == 0) {
+                    const int ea = (int)(pk & 0xffffu), eb = (int)((pk >> 16) & 0xffffu), ec = (int)((pk >> 32) & 0xffffu);
+                    const float ma = msg[ea], mb = msg[eb], mc = msg[ec];
+                    const float total = sllr[pi] + ((ma + mb) + mc);
+                    msg[ea] = total - ma;
+                    msg[eb] = total - mb;
+                    msg[ec] = total - mc;
+                    bit = (total <= 0.0f);
+                    if (P.total != nullptr) P.total[f * n + P.varof[pi]] = total;
+                }
+                if (want_hard) {
+                    const unsigned bal = __ballot_sync(PCL_FULL_MASK, bit);
+                    if (lane == 0) hard[vb >> 5] = bal;
+                }
+            }
+            sync();
+            // 4. syndrome early stop
+            if (Y.early_stop) {
+                bool bad = false;
+                for (int R = w0; R < nR; R += wstep) {
+                    unsigned par = 0;
+#pragma unroll
+                    for (int k = 0; k < DC; k++) {
+                        const int cp = P.cpos[32 * (DC * R + k) + lane];
+                        if (cp != 0xffff) par ^= hard[cp >> 5] >> (cp & 31);
+                    }
+                    bad |= (par & 1u) != 0;
+                }
+                bool any_bad = __any_sync(PCL_FULL_MASK, bad);
+                if (coop) {
+                    if (tid == 0) ctl[1] = 0ull;
+                    __syncthreads();
+                    if (any_bad && lane == 0) ctl[1] = 1ull;
+                    __syncthreads();
+                    any_bad = ctl[1] != 0ull;
+                }
+                if (!any_bad) { iters = it + 1; break; }
+            }
+        }
+        uint8_t* outb = P.bits + f * n;
+        for (int v = tid; v < n; v += T) {
+            const int pi = P.posof[v];
+            outb[v] = (uint8_t)((hard[pi >> 5] >> (pi & 31)) & 1u);
+        }
+        if (P.iters != nullptr && tid == 0) P.iters[f] = iters;
+        sync();
+    }
+}

@@ -34,6 +34,7 @@ struct LdpcLayout {
     int nhw;                    // hard-decision words = ceil(n / 32)
     int off_msg, off_llr, off_hard, off_ctl, warp_bytes;
     int coop;                   // 1: the whole block decodes one frame (large codes), 0: one warp per frame
+    int banked, nR, NP, NS;     // banked layout (ldpc_banked_kernel): check rounds, variable positions, slots
 };
 
 template <typename real>
@@ -48,6 +49,10 @@ struct LdpcParams {
     const int32_t* vptr;        // [n+1]
     const uint16_t* vperm;      // [E] edge ids, variable-major
     const unsigned long long* vpack;  // REG: per variable, its 3 edge ids packed 16 bits each
+    const unsigned long long* bpack;  // banked: per variable position, its 3 slots (bits 48.. set: hole)
+    const uint16_t* varof;      // banked: variable at position pi (0xffff: hole)
+    const uint16_t* posof;      // banked: position of variable v
+    const uint16_t* cpos;       // banked: variable position behind slot s (0xffff: hole)
     unsigned long long* next;   // dynamic frame counter
     int64_t F;
     real norm;                  // Min-Sum normalisation
@@ -141,31 +146,19 @@ PCL_DEVICE float pcl_rcp(float x)
 #endif
 }
 
-// VEC2: the check's DMAX messages start at an 8-byte boundary and all exist (regular codes):
-// 8-byte shared-memory accesses, conflict-free at a stride of 6 words.
-template <int DMAX, bool VEC2>
-PCL_DEVICE void cn_bp_f32(float* msg, int d)
+// Register-level rule: xb = bit patterns of the DMAX incoming messages (ALL: every one exists,
+// else the first d), out = outgoing messages.
+template <int DMAX, bool ALL>
+PCL_DEVICE void cn_bp_core(const uint32_t* xb, float* out, int d)
 {
     const float UMIN = 5.00000250000125e-07f, RMAX = 1999999.0f;
     float u[DMAX];
-    uint32_t xb[DMAX];
     uint32_t sall = 0;
-    if (VEC2) {
-#pragma unroll
-        for (int j = 0; j < DMAX; j += 2) {
-            const float2 v = reinterpret_cast<const float2*>(msg)[j >> 1];
-            xb[j] = __float_as_uint(v.x);
-            xb[j + 1] = __float_as_uint(v.y);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < DMAX; j++) xb[j] = (j < d) ? __float_as_uint(msg[j]) : 0x7f800000u;   // +inf: u = 0
-    }
 #pragma unroll
     for (int j = 0; j < DMAX; j++) {
         const float ax = fabsf(__uint_as_float(xb[j]));
         const float e = pcl_ex2(ax * -1.4426950408889634f);           // exp(-|x|), rel. err ~ |x| * 6e-8
-        u[j] = (VEC2 || j < d) ? fmaxf(e, UMIN) : 0.0f;
+        u[j] = (ALL || j < d) ? fmaxf(e, UMIN) : 0.0f;
         sall ^= xb[j];
     }
     // suffix pairs, then a running prefix pair
@@ -178,7 +171,6 @@ PCL_DEVICE void cn_bp_f32(float* msg, int d)
         so[j] = fmaf(u[j], se[j + 1], so[j + 1]);
     }
     float pe = 1.0f, po = 0.0f;
-    float out[DMAX];
 #pragma unroll
     for (int i = 0; i < DMAX; i++) {
         const float E = fmaf(po, so[i + 1], pe * se[i + 1]);
@@ -190,6 +182,27 @@ PCL_DEVICE void cn_bp_f32(float* msg, int d)
         po = fmaf(u[i], pe, po);
         pe = npe;
     }
+}
+
+// VEC2: the check's DMAX messages start at an 8-byte boundary and all exist (regular codes):
+// 8-byte shared-memory accesses, conflict-free at a stride of 6 words.
+template <int DMAX, bool VEC2>
+PCL_DEVICE void cn_bp_f32(float* msg, int d)
+{
+    uint32_t xb[DMAX];
+    float out[DMAX];
+    if (VEC2) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j += 2) {
+            const float2 v = reinterpret_cast<const float2*>(msg)[j >> 1];
+            xb[j] = __float_as_uint(v.x);
+            xb[j + 1] = __float_as_uint(v.y);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) xb[j] = (j < d) ? __float_as_uint(msg[j]) : 0x7f800000u;   // +inf: u = 0
+    }
+    cn_bp_core<DMAX, VEC2>(xb, out, d);
     if (VEC2) {
 #pragma unroll
         for (int j = 0; j < DMAX; j += 2) {
@@ -248,10 +261,32 @@ template <> struct ldpc_bits<double> {
 };
 
 template <typename real, int DMAX>
-PCL_DEVICE void cn_ms_reg(real* msg, real norm)
+PCL_DEVICE void cn_ms_core(const real* x, real* out, real norm)
 {
     typedef typename ldpc_bits<real>::u bits_t;
-    real x[DMAX], a[DMAX];
+    real a[DMAX];
+    bits_t sall = 0;
+    real m1 = pcl_math<real>::inf(), m2 = pcl_math<real>::inf();
+#pragma unroll
+    for (int j = 0; j < DMAX; j++) {
+        a[j] = fabs(x[j]);
+        // np.sign: a NaN-free input is negative iff x < 0 (-0.0 is not)
+        sall ^= (x[j] < (real)0) ? ldpc_bits<real>::sign() : (bits_t)0;
+        m2 = fmin(m2, fmax(m1, a[j]));
+        m1 = fmin(m1, a[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+        const real mn = (a[i] > m1) ? m1 : m2;
+        const bits_t sg = sall ^ ((x[i] < (real)0) ? ldpc_bits<real>::sign() : (bits_t)0);
+        out[i] = ldpc_bits<real>::to(ldpc_bits<real>::of(mn * norm) ^ sg);       // (+-1 * min) * norm, :285
+    }
+}
+
+template <typename real, int DMAX>
+PCL_DEVICE void cn_ms_reg(real* msg, real norm)
+{
+    real x[DMAX], out[DMAX];
     if (sizeof(real) == 4 && DMAX % 2 == 0) {
 #pragma unroll
         for (int j = 0; j < DMAX; j += 2) {
@@ -263,23 +298,7 @@ PCL_DEVICE void cn_ms_reg(real* msg, real norm)
 #pragma unroll
         for (int j = 0; j < DMAX; j++) x[j] = msg[j];
     }
-    bits_t sall = 0;
-    real m1 = pcl_math<real>::inf(), m2 = pcl_math<real>::inf();
-#pragma unroll
-    for (int j = 0; j < DMAX; j++) {
-        a[j] = fabs(x[j]);
-        // np.sign: a NaN-free input is negative iff x < 0 (-0.0 is not)
-        sall ^= (x[j] < (real)0) ? ldpc_bits<real>::sign() : (bits_t)0;
-        m2 = fmin(m2, fmax(m1, a[j]));
-        m1 = fmin(m1, a[j]);
-    }
-    real out[DMAX];
-#pragma unroll
-    for (int i = 0; i < DMAX; i++) {
-        const real mn = (a[i] > m1) ? m1 : m2;
-        const bits_t sg = sall ^ ((x[i] < (real)0) ? ldpc_bits<real>::sign() : (bits_t)0);
-        out[i] = ldpc_bits<real>::to(ldpc_bits<real>::of(mn * norm) ^ sg);       // (+-1 * min) * norm, :285
-    }
+    cn_ms_core<real, DMAX>(x, out, norm);
     if (sizeof(real) == 4 && DMAX % 2 == 0) {
 #pragma unroll
         for (int j = 0; j < DMAX; j += 2) {

@@ -9,6 +9,8 @@
 #include "polar_scl.cuh"
 #include "polar_scl_fast.cuh"
 #include "framegen.cuh"
+#include "ldpc_banked.cuh"
+#include "ldpc_layout.h"
 #include "ldpc_bp.cuh"
 #include "../../include/pcl.h"
 
@@ -437,6 +439,11 @@ struct pcl_ldpc {
     int32_t* d_vptr = nullptr;
     uint16_t* d_vperm = nullptr;
     unsigned long long* d_vpack = nullptr;
+    unsigned long long* d_bpack = nullptr;      // banked layout tables (ldpc_layout.h)
+    uint16_t* d_varof = nullptr;
+    uint16_t* d_posof = nullptr;
+    uint16_t* d_cpos = nullptr;
+    int banked_residual = 0;
     unsigned long long* d_next[PCL_NSTAGE] = {};
     int wpb, grid_max, smem_bytes, last_grid = 0;
     void* d_llr[PCL_NSTAGE] = {};
@@ -451,6 +458,12 @@ struct pcl_ldpc {
 template <typename real, int COOP, typename Fn>
 static int ldpc_with_kernel_c(pcl_ldpc* h, Fn&& fn)
 {
+    if constexpr (sizeof(real) == 4) {
+        if (h->lay.banked) {
+            if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, COOP>);
+            return fn(ldpc_banked_kernel<0, 6, COOP>);
+        }
+    }
     if (h->mode == PCL_LDPC_MS) {
         if (h->regular6) return fn(ldpc_decode_kernel<real, 1, 6, 1, COOP>);
         return fn(ldpc_decode_kernel<real, 1, 8, 0, COOP>);
@@ -544,10 +557,24 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     LdpcLayout& Y = h->lay;
     Y.m = m; Y.n = n; Y.E = E; Y.max_iter = max_iter; Y.early_stop = h->early_stop;
     Y.nhw = (n + 31) / 32;
+    // fp32 production build, regular (3, 6) codes: conflict-free banked layout (ldpc_banked.cuh)
+    BankedLayout bl;
+    Y.banked = 0; Y.nR = 0; Y.NP = 0; Y.NS = 0;
+    if (h->regular6 && dtype == PCL_F32 && E > 0 && env_int("PCL_LDPC_BANKED", 1) != 0) {
+        std::vector<int> var_checks(3 * (size_t)n), check_vars(6 * (size_t)m);
+        for (int v = 0; v < n; v++)
+            for (int j = 0; j < 3; j++) var_checks[3 * v + j] = vperm[vptr[v] + j] / 6;   // edge e belongs to check e / 6
+        for (int e = 0; e < E; e++) check_vars[e] = col[e];
+        const long budget = std::min<long>(16000000L, 2700L * E);
+        if (build_banked_layout(m, n, 6, var_checks, check_vars, env_int("PCL_LDPC_ANNEAL", (int)budget), &bl)) {
+            Y.banked = 1; Y.nR = bl.nR; Y.NP = bl.NP; Y.NS = bl.NS;
+            h->banked_residual = bl.residual;
+        }
+    }
     int off = 0;
-    Y.off_msg = off;  off += align_up(std::max(E, 1) * rsz, 8);
-    Y.off_llr = off;  off += align_up(n * rsz, 8);
-    Y.off_hard = off; off += align_up(Y.nhw * 4, 8);
+    Y.off_msg = off;  off += align_up((Y.banked ? Y.NS : std::max(E, 1)) * rsz, 8);
+    Y.off_llr = off;  off += align_up((Y.banked ? Y.NP : n) * rsz, 8);
+    Y.off_hard = off; off += align_up((Y.banked ? Y.NP / 32 : Y.nhw) * 4, 8);
     Y.off_ctl = off;  off += 16;
     Y.warp_bytes = align_up(off, 16);
 
@@ -607,6 +634,16 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
         ok = cudaMalloc((void**)&h->d_vpack, (size_t)n * 8) == cudaSuccess &&
              cudaMemcpy(h->d_vpack, vpack.data(), (size_t)n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    if (ok && Y.banked) {
+        ok = cudaMalloc((void**)&h->d_bpack, (size_t)Y.NP * 8) == cudaSuccess &&
+             cudaMalloc((void**)&h->d_varof, (size_t)Y.NP * 2) == cudaSuccess &&
+             cudaMalloc((void**)&h->d_posof, (size_t)n * 2) == cudaSuccess &&
+             cudaMalloc((void**)&h->d_cpos, (size_t)Y.NS * 2) == cudaSuccess &&
+             cudaMemcpy(h->d_bpack, bl.bpack.data(), (size_t)Y.NP * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(h->d_varof, bl.varof.data(), (size_t)Y.NP * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(h->d_posof, bl.posof.data(), (size_t)n * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(h->d_cpos, bl.cpos.data(), (size_t)Y.NS * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) { pcl_ldpc_destroy(h); return fail(PCL_ECUDA, "device table setup failed"); }
     *out = h;
     return PCL_OK;
@@ -616,6 +653,7 @@ extern "C" void pcl_ldpc_destroy(pcl_ldpc_t* h)
 {
     if (!h) return;
     cudaFree(h->d_cptr); cudaFree(h->d_col); cudaFree(h->d_vptr); cudaFree(h->d_vperm); cudaFree(h->d_vpack);
+    cudaFree(h->d_bpack); cudaFree(h->d_varof); cudaFree(h->d_posof); cudaFree(h->d_cpos);
     for (int s = 0; s < PCL_NSTAGE; s++) {
         cudaFree(h->d_next[s]); cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
 #ifndef PCL_EMU
@@ -647,6 +685,7 @@ static int ldpc_decode_impl(pcl_ldpc* h, const void* llr_dev, int64_t F, uint8_t
     P.iters = iters_dev;
     P.total = (real*)total_dev;
     P.cptr = h->d_cptr; P.col = h->d_col; P.vptr = h->d_vptr; P.vperm = h->d_vperm; P.vpack = h->d_vpack;
+    P.bpack = h->d_bpack; P.varof = h->d_varof; P.posof = h->d_posof; P.cpos = h->d_cpos;
     P.next = next;
     P.F = F;
     P.norm = (real)h->norm;
