@@ -100,6 +100,10 @@ int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t
                          int32_t* iters_host, void* stream);
 int pcl_ldpc_num_edges(const pcl_ldpc_t* h);
 int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, int* smem_bytes);
+/* Shared-memory layout in use: *banked = 1 for the conflict-free layout of regular (3, 6) codes in
+ * the fp32 build (*residual = message fetches that still share a bank, per iteration), *coop = 1
+ * when a whole block decodes one frame (large codes). */
+int pcl_ldpc_layout_info(const pcl_ldpc_t* h, int* banked, int* residual, int* coop);
 
 /*
  * On-device frame generation for BER / FER sweeps: the per-frame pipeline of the reference's

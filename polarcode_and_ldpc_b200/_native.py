@@ -52,6 +52,7 @@ def lib() -> ctypes.CDLL:
     L.pcl_ldpc_decode_host.argtypes = [vp, vp, i64, vp, vp, vp]
     L.pcl_ldpc_num_edges.argtypes = [vp]
     L.pcl_ldpc_launch_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 3
+    L.pcl_ldpc_layout_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 3
     L.pcl_count_errors.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     L.pcl_gen_polar_create.argtypes = [ctypes.POINTER(vp), i32, i32, vp]
     L.pcl_gen_ldpc_create.argtypes = [ctypes.POINTER(vp), i32, i32, vp]
@@ -70,7 +71,7 @@ EXPORTS = [
     "pcl_polar_create", "pcl_polar_destroy", "pcl_polar_decode_batch", "pcl_polar_decode_host",
     "pcl_polar_lp", "pcl_polar_launch_info",
     "pcl_ldpc_create", "pcl_ldpc_destroy", "pcl_ldpc_decode_batch", "pcl_ldpc_decode_host",
-    "pcl_ldpc_num_edges", "pcl_ldpc_launch_info", "pcl_count_errors",
+    "pcl_ldpc_num_edges", "pcl_ldpc_launch_info", "pcl_ldpc_layout_info", "pcl_count_errors",
     "pcl_gen_polar_create", "pcl_gen_ldpc_create", "pcl_gen_destroy", "pcl_gen_frames", "pcl_gen_frames_channel", "pcl_philox4x32_10_host",
 ]
 

@@ -13,11 +13,12 @@
 //     the 32 words one instruction touches lie in 32 different banks (bank = l).  (a), (b) come
 //     from a short annealing run at handle creation (a round's 96 edges must hit every bank
 //     exactly 3 times), (c) from recolouring; the few edges that cannot be placed cost one extra
-//     wavefront each (3 of 1512 for the n = 504 code).
+//     wavefront each (about 11 of the 1512 fetches of a pass for the n = 504 code).
 // Hard decisions, the channel LLRs and the syndrome test live in position space; `varof` /
 // `posof` translate at frame load and store.  The variable sum adds its three messages in
-// instruction order, not in ascending check order (fp32 build only; the fp64 validation build
-// keeps ldpc_bp.cuh and the reference's order).
+// instruction order, not in ascending check order, and BP messages are carried in units of ln 2
+// (one multiply less on each side of the check rule); both fp32 build only -- the fp64 validation
+// build keeps ldpc_bp.cuh, the reference's order and its units.
 #pragma once
 #include "ldpc_bp.cuh"
 
@@ -58,7 +59,8 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
         const float* ch = P.llr + f * n;
         for (int pi = tid; pi < NP; pi += T) {
             const int v = P.varof[pi];
-            sllr[pi] = (v != 0xffff) ? ch[v] : 0.0f;
+            // BP carries every message in units of ln 2 (cn_bp_core<.., LOG2>): scale the channel once
+            sllr[pi] = (v != 0xffff) ? ch[v] * (MODE == 0 ? 1.4426950408889634f : 1.0f) : 0.0f;
         }
         sync();
         for (int s = tid; s < NS; s += T) {                            // decoder.py:144-146
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
                     uint32_t xb[DC];
 #pragma unroll
                     for (int k = 0; k < DC; k++) xb[k] = __float_as_uint(base[32 * k]);
-                    cn_bp_core<DC, true>(xb, out, DC);
+                    cn_bp_core<DC, true, true>(xb, out, DC);
                 }
 #pragma unroll
                 for (int k = 0; k < DC; k++) base[32 * k] = out[k];
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
                     msg[eb] = total - mb;
                     msg[ec] = total - mc;
                     bit = (total <= 0.0f);
-                    if (P.total != nullptr) P.total[f * n + P.varof[pi]] = total;
+                    if (P.total != nullptr) P.total[f * n + P.varof[pi]] = total * (MODE == 0 ? 0.6931471805599453f : 1.0f);
                 }
                 if (want_hard) {
                     const unsigned bal = __ballot_sync(PCL_FULL_MASK, bit);

@@ -148,7 +148,12 @@ PCL_DEVICE float pcl_rcp(float x)
 
 // Register-level rule: xb = bit patterns of the DMAX incoming messages (ALL: every one exists,
 // else the first d), out = outgoing messages.
-template <int DMAX, bool ALL>
+// LOG2: the messages are carried in units of ln 2 (y = x / ln 2), so u = 2^-|y| and the output is
+// lg2(E / O) with no scaling multiply on either side (the variable pass is linear, the channel
+// LLRs are scaled once per frame).  With ALL and DMAX >= 3 the output clip can never act: every
+// u >= 5e-7 makes O >= 1e-6 E, i.e. E / O < 1999999 (the reference's second clip, decoder.py:88,
+// is likewise unreachable after the first one for checks of degree >= 3).
+template <int DMAX, bool ALL, bool LOG2 = false>
 PCL_DEVICE void cn_bp_core(const uint32_t* xb, float* out, int d)
 {
     const float UMIN = 5.00000250000125e-07f, RMAX = 1999999.0f;
@@ -157,7 +162,7 @@ PCL_DEVICE void cn_bp_core(const uint32_t* xb, float* out, int d)
 #pragma unroll
     for (int j = 0; j < DMAX; j++) {
         const float ax = fabsf(__uint_as_float(xb[j]));
-        const float e = pcl_ex2(ax * -1.4426950408889634f);           // exp(-|x|), rel. err ~ |x| * 6e-8
+        const float e = LOG2 ? pcl_ex2(-ax) : pcl_ex2(ax * -1.4426950408889634f);   // exp(-|x|), rel. err ~ |x| * 6e-8
         u[j] = (ALL || j < d) ? fmaxf(e, UMIN) : 0.0f;
         sall ^= xb[j];
     }
@@ -175,8 +180,9 @@ PCL_DEVICE void cn_bp_core(const uint32_t* xb, float* out, int d)
     for (int i = 0; i < DMAX; i++) {
         const float E = fmaf(po, so[i + 1], pe * se[i + 1]);
         const float O = fmaf(po, se[i + 1], pe * so[i + 1]);
-        const float ratio = fminf(E * pcl_rcp(O), RMAX);
-        const float mag = 0.6931471805599453f * pcl_lg2(ratio);
+        const float r0 = E * pcl_rcp(O);
+        const float ratio = (ALL && DMAX >= 3 && LOG2) ? r0 : fminf(r0, RMAX);
+        const float mag = LOG2 ? pcl_lg2(ratio) : 0.6931471805599453f * pcl_lg2(ratio);
         out[i] = __uint_as_float(__float_as_uint(mag) | ((sall ^ xb[i]) & 0x80000000u));
         const float npe = fmaf(u[i], po, pe);
         po = fmaf(u[i], pe, po);

@@ -665,6 +665,15 @@ extern "C" void pcl_ldpc_destroy(pcl_ldpc_t* h)
 
 extern "C" int pcl_ldpc_num_edges(const pcl_ldpc_t* h) { return h ? h->E : 0; }
 
+extern "C" int pcl_ldpc_layout_info(const pcl_ldpc_t* h, int* banked, int* residual, int* coop)
+{
+    if (!h) return fail(PCL_EINVAL, "null handle");
+    if (banked) *banked = h->lay.banked;
+    if (residual) *residual = h->banked_residual;
+    if (coop) *coop = h->lay.coop;
+    return PCL_OK;
+}
+
 extern "C" int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, int* smem_bytes)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
