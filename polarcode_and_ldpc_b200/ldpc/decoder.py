@@ -131,8 +131,12 @@ class _LdpcBase:
     def launch_info(self) -> dict:
         g, b, s = (ctypes.c_int() for _ in range(3))
         _native.check(_native.lib().pcl_ldpc_launch_info(self._h, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
+        bk, rs, cp = (ctypes.c_int() for _ in range(3))
+        _native.check(_native.lib().pcl_ldpc_layout_info(self._h, ctypes.byref(bk), ctypes.byref(rs), ctypes.byref(cp)))
         return {"grid": g.value, "block": b.value, "smem_bytes": s.value,
-                "edges": _native.lib().pcl_ldpc_num_edges(self._h)}
+                "edges": _native.lib().pcl_ldpc_num_edges(self._h),
+                "kernel": "ldpc_banked_kernel" if bk.value else "ldpc_decode_kernel",
+                "bank_conflicts_per_pass": rs.value if bk.value else None, "block_per_frame": bool(cp.value)}
 
 
 class BPDecoder(_LdpcBase):

@@ -243,6 +243,29 @@ def test_ldpc_warp_and_block_per_frame_agree(coop):
         os.environ.pop("PCL_LDPC_COOP")
 
 
+def test_ldpc_layout_selection():
+    """Regular (3,6) codes in the fp32 build run the conflict-free layout (a handful of residual
+    bank conflicts per pass); fp64, irregular codes and PCL_LDPC_BANKED=0 keep the check-major
+    one; codes with n >= 1008 are decoded by a block per frame."""
+    H = P.gallager_parity_check(504, 3, 6, 42)
+    info = P.BPDecoder(H, max_iter=5).launch_info()
+    assert info["kernel"] == "ldpc_banked_kernel" and info["bank_conflicts_per_pass"] <= 24 and not info["block_per_frame"]
+    assert P.BPDecoder(H, max_iter=5, dtype="float64").launch_info()["kernel"] == "ldpc_decode_kernel"
+    assert P.BPDecoder(P.mackay_parity_check(504, 252, 3, 6, seed=42), max_iter=5).launch_info()["kernel"] == "ldpc_decode_kernel"
+    assert P.MSDecoder(P.gallager_parity_check(2016, 3, 6, 42), max_iter=5).launch_info()["block_per_frame"]
+    os.environ["PCL_LDPC_BANKED"] = "0"
+    try:
+        np.random.seed(5)
+        llr = P.AWGNChannel(1.0).transmit_batch(np.zeros((512, 504), dtype=int))
+        a, ia = P.BPDecoder(H, max_iter=20).decode_batch(llr, return_iterations=True)
+        assert P.BPDecoder(H, max_iter=20).launch_info()["kernel"] == "ldpc_decode_kernel"
+    finally:
+        os.environ.pop("PCL_LDPC_BANKED")
+    b, ib = P.BPDecoder(H, max_iter=20).decode_batch(llr, return_iterations=True)
+    rb, ri = oracle.ldpc(H, llr, "bp", max_iter=20, nthreads=8)
+    assert np.array_equal(a, rb) and np.array_equal(b, rb) and np.array_equal(ia, ri) and np.array_equal(ib, ri)
+
+
 def test_ldpc_irregular_inrepo_H():
     """The in-repo mackay construction (rows of degree 0..13) used by throughput_test.py:285."""
     H = P.mackay_parity_check(504, 252, 3, 6, seed=42)
