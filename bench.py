@@ -87,15 +87,32 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons / power sampled DURING the timed region.  NVML through
+    nvidia_ml_py in a thread (a query costs microseconds and does not disturb the kernels; a
+    polling `nvidia-smi -lms` process was seen to slow individual steps by 10-30 %); falls back
+    to nvidia-smi when the module is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.stop_flag, self.thread = None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (pynvml, h)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -105,22 +122,44 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((sm, mask, pw))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = [r[0] for r in self.rows]
+            reasons = [n for n in self.NAMES if any(r[1] & self.BITS[n] for r in self.rows)]
+            pw = [r[2] for r in self.rows]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons, "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ inputs ------
