@@ -291,6 +291,10 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     if (rc) { delete h; return rc; }
     if (bps < 1) { delete h; return fail(PCL_ECUDA, "kernel does not fit on an SM"); }
 #endif
+    {
+        const int cap = env_int("PCL_POLAR_BPS", 0);     // experiment knob: resident blocks per SM
+        if (cap > 0 && cap < bps) bps = cap;
+    }
     h->grid_max = di.sms * bps;
     h->scratch_bytes = (size_t)h->grid_max * h->wpb * h->lay.scratch_per_warp * rsz;
 
