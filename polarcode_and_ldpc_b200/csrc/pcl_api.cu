@@ -210,6 +210,16 @@ static int polar_occ(pcl_polar* h, int threads, int smem, int* bps)
     return polar_with_kernel<real>(h, [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem));
+        // Ask for the shared-memory carve-out the computed residency needs.  Left to its default the
+        // driver may keep the split of the kernel that ran before (seen after the polar kernel: half
+        // the LDPC blocks per SM and half the throughput in some runs of the same binary).
+        DeviceInfo di2;
+        if (device_info(&di2) == PCL_OK && *bps > 0) {
+            long need = (long)(*bps) * (smem + 1024);
+            int pct = (int)((need * 100 + di2.smem_per_sm - 1) / di2.smem_per_sm);
+            if (pct > 100) pct = 100;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
         return PCL_OK;
     });
 }
@@ -505,6 +515,16 @@ static int ldpc_occ(pcl_ldpc* h, int threads, int smem, int* bps)
     return ldpc_with_kernel<real>(h, [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem));
+        // Ask for the shared-memory carve-out the computed residency needs.  Left to its default the
+        // driver may keep the split of the kernel that ran before (seen after the polar kernel: half
+        // the LDPC blocks per SM and half the throughput in some runs of the same binary).
+        DeviceInfo di2;
+        if (device_info(&di2) == PCL_OK && *bps > 0) {
+            long need = (long)(*bps) * (smem + 1024);
+            int pct = (int)((need * 100 + di2.smem_per_sm - 1) / di2.smem_per_sm);
+            if (pct > 100) pct = 100;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
         return PCL_OK;
     });
 }
