@@ -80,10 +80,11 @@ if __name__ == "__main__":
     ap.add_argument("--polar-N", type=int, default=128)
     ap.add_argument("--polar-K", type=int, default=64)
     ap.add_argument("--ldpc-n", type=int, default=120)
+    ap.add_argument("--ldpc-iters", type=int, default=50)
     ap.add_argument("--snr", default="0,6,1")
     ap.add_argument("--output-dir", default=str(Path(__file__).parent.parent / "results"))
     a = ap.parse_args()
     s0, s1, ds = (float(x) for x in a.snr.split(","))
     polar_config = {"encoding": {"N": a.polar_N, "K": a.polar_K}, "construction": {"design_snr_db": 2.0}}
-    ldpc_config = {"encoding": {"n": a.ldpc_n, "k": a.ldpc_n // 2, "dv": 3, "dc": 6}, "decoding": {"max_iterations": 50}}
+    ldpc_config = {"encoding": {"n": a.ldpc_n, "k": a.ldpc_n // 2, "dv": 3, "dc": 6}, "decoding": {"max_iterations": a.ldpc_iters}}
     run_ber_simulation(np.arange(s0, s1, ds), a.num_frames, a.max_errors, polar_config, ldpc_config, Path(a.output_dir))
