@@ -21,4 +21,19 @@ for n in (96,504):
         for dt in ('f32','f64'):
             emu.ldpc_decode(H,llr,mode,6,0.75,True,dt,want_total=True)
 Hm=P.mackay_parity_check(120,60,3,6,seed=42); emu.ldpc_decode(Hm,rng.normal(1,2,size=(3,120)),'bp',5)
+# block-per-frame mode and the check-major layout in the fp32 build
+for env in ({'PCL_LDPC_COOP':'1'},{'PCL_LDPC_BANKED':'0'},{'PCL_LDPC_COOP':'1','PCL_LDPC_BANKED':'0'}):
+    os.environ.update(env)
+    H=P.gallager_parity_check(96,3,6,42)
+    for mode in ('bp','ms'):
+        emu.ldpc_decode(H,rng.normal(1,2.5,size=(3,96)),mode,4,0.75,True,'f32',want_total=True)
+    for k in env: os.environ.pop(k)
+# frame generator: polar / LDPC, every channel, odd sizes
+for N,K in ((16,7),(64,33),(1024,512),(2048,1000)):
+    fz=P.bhattacharyya_frozen_set(N,K,2.0)
+    for ch in (0,1,2):
+        emu.gen_frames('polar',N,K,fz,5,0.1 if ch==2 else 1.5,seed=3,frame0=7,channel=ch,dtype='f64' if ch==1 else 'f32')
+for n in (96,504):
+    H=P.gallager_parity_check(n,3,6,42); G,_=P.generator_from_parity(H)
+    emu.gen_frames('ldpc',n,G.shape[0],G,5,1.0,seed=4)
 print('asan run ok')
