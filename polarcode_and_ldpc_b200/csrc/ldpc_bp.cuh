@@ -17,14 +17,13 @@
 // fp64 build: the reference's arithmetic and association order exactly
 // (tanh -> clip -> left-to-right leave-one-out product -> clip -> 2 atanh;
 // numpy's pairwise np.sum order for the variable sum).
-// fp32 build: same schedule, but the check rule carries w = 1 - |tanh(x/2)| next
-// to t so that messages saturating towards +-1 keep full relative precision
-// (the 0.999999 clip sits where d atanh/dp ~ 5e5; a 1-ulp fp32 error in p would
-// be a 4e-3 relative error in the outgoing LLR); signs and
-// magnitudes travel separately and each edge costs four MUFU ops (ex2, rcp in; rcp,
-// lg2 out).  The kernel is issue-bound (ncu: ~89 % issue-slot utilisation, 49 k warp
-// instructions per n=504, 20-iteration frame); regular (3, 6) codes get compile-time
-// degrees (REG) and packed per-variable edge ids.
+// fp32 build: same schedule; the check rule works on u = exp(-|x|) and the even / odd
+// elementary symmetric sums of the u_j (cn_bp_core below: no cancellation for saturated or
+// weak messages, three MUFU ops per edge); signs travel as an XOR of sign bits.  Regular
+// (3, 6) codes get compile-time degrees (REG) and, in the fp32 build, the conflict-free layout of
+// ldpc_banked.cuh; this kernel serves the fp64 validation build, irregular codes and
+// PCL_LDPC_BANKED=0.  COOP: codes too large for ~16 resident frames per SM are decoded by a
+// block of 4 warps per frame with block barriers between the passes.
 #pragma once
 #include "pcl_common.cuh"
 

@@ -2,7 +2,7 @@
 // frames per warp.  Production kernel for N >= 16 (polar_scl.cuh is the fallback).
 //
 // Same algorithm, list semantics and pointer scheme as polar_scl.cuh (read that header
-// first).  What differs, each step driven by an ncu capture (profiles/r01a .. r01k):
+// first).  What differs, each step driven by an ncu capture (profiles/r01a .. r01o):
 //   * A lane owns a whole path and a warp decodes FPW = 32 / LP frames side by side (4 frames
 //     at L = 8).  All frames of a warp follow the same schedule (frozen pattern, number of live
 //     paths), so every branch is warp-uniform and the per-leaf bookkeeping instructions are
@@ -28,6 +28,14 @@
 //     the fp64 metric, so one DSETP + one predicated add per pair gives both the metric order
 //     and the reference's tie order, and the survivor scatter moves the key alone (the id comes
 //     back out of it); fp64 build keeps the exact two-key comparison and the exact metric.
+//     Reliable info bits never get that far (fp32 build): on a full list whose likely keys are
+//     still in slot order, with every unlikely key below the last of them, each path continues
+//     in place (80 % of the info leaves at 2 dB); otherwise the ranks against the likely keys
+//     come first and the unlikely half is skipped when none of them can survive.  Both give
+//     exactly the survivors and slots of the full ranking.
+//   * The warps of a block make the same number of frame passes and meet at a barrier before
+//     each: identical instruction streams keep them at the same tree position, so a block
+//     shares one instruction working set (the hot code is ~40 KB, the instruction cache 32 KB).
 // Path metric in fp64; fp32 build evaluates log1p(exp(-|x|)) as 2 atanh(u / (2 + u)) with
 // u = 2^(-|x| log2 e) (one ex2, one rcp, 6 FMA; |error| < 1e-7).
 #pragma once
