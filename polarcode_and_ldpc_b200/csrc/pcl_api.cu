@@ -160,8 +160,12 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
 #else
 #define PCL_POLAR_FAST_VARIANTS(X) \
     X(1, 0, 0) X(2, 0, 0) X(4, 0, 0) X(8, 0, 0) X(16, 0, 0) X(32, 0, 0) \
-    X(1, 10, 5) X(8, 10, 5) X(32, 10, 5) X(1, 8, 2) X(8, 8, 2)
+    X(8, 7, 1) X(8, 8, 2) X(8, 9, 4) X(8, 10, 5) X(8, 11, 7) X(8, 12, 8) X(32, 10, 5) X(1, 8, 2)
 #endif
+// (SCL-8 gains 1.2-1.9 x from a compiled code length at every N = 128 .. 4096.  SC, LP = 1, does
+// not in general -- N = 1024: 29 Gbps compiled vs 40 at run time; with no prune its time is all
+// level walk and the unrolled walk is bigger code -- so only the N = 256 quick-start size of
+// BASELINE configs[0] keeps one: 47 vs 41 Gbps at the bench's batch of 524 288 frames.)
 
 static bool polar_fast_variant_exists(int LP, int nl, int gl)
 {
@@ -175,7 +179,10 @@ template <typename real, typename Fn>
 static int polar_with_kernel(pcl_polar* h, Fn&& fn)
 {
     if (h->fast) {
-#define X(lp, n_, g_) if (h->LP == lp && h->NL == n_ && h->GL == g_) return fn(polar_scl_fast_kernel<lp, real, n_, g_>);
+#define X(lp, n_, g_)                                                                          \
+    if constexpr (n_ == 0 || sizeof(real) == 4) {                                                   \
+        if (h->LP == lp && h->NL == n_ && h->GL == g_) return fn(polar_scl_fast_kernel<lp, real, n_, g_>); \
+    }
         PCL_POLAR_FAST_VARIANTS(X)
 #undef X
     } else {
@@ -288,7 +295,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     if (G < gmin) G = gmin;
     polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
     h->NL = 0; h->GL = 0;
-    if (h->fast && env_int("PCL_POLAR_NL", 1) != 0 && polar_fast_variant_exists(LP, n, G)) { h->NL = n; h->GL = G; }
+    // code lengths with log2 N and G compiled in (fp32 build; the validation build reads them at run time)
+    if (h->fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && polar_fast_variant_exists(LP, n, G)) { h->NL = n; h->GL = G; }
     h->smem_bytes = h->lay.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
         delete h;

@@ -431,7 +431,7 @@ def test_generic_kernel_fallback_matches(golden_dir):
 @pytest.mark.parametrize("NL", [1, 0])
 def test_compiled_code_length_variants(NL):
     """PCL_POLAR_NL=0 forces the kernel that reads log2 N and G at run time; 1 (default) lets
-    the library pick the variants compiled for N = 1024 / 256.  Both must give the oracle's
+    the library pick the variants compiled for list size 8 (N = 128 .. 4096) and 32 (N = 1024).  Both must give the oracle's
     bits, also for batches that leave a warp partly empty and for code lengths without a
     compiled variant."""
     S = NL
@@ -448,7 +448,7 @@ def test_compiled_code_length_variants(NL):
                 got = dec.decode_batch(llr)
                 bad = int((got != ref).any(axis=1).sum())
                 assert bad == 0 if dt == "float64" else bad <= 1, f"N={N} L={L} NL={NL} {dt}: {bad} frames differ"
-                if NL and dt == "float32" and (N, L) in ((1024, 8), (1024, 32), (256, 8)):
+                if NL and dt == "float32" and (N, L) in ((1024, 8), (1024, 32), (256, 8), (512, 8), (2048, 8)):
                     assert dec.launch_info()["compiled_code_length"]
     finally:
         os.environ.pop("PCL_POLAR_NL")
