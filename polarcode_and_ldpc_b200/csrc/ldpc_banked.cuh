@@ -22,7 +22,11 @@
 #pragma once
 #include "ldpc_bp.cuh"
 
-template <int MODE, int DC, int COOP>
+// PAIRED: the k-th message of the check at (R, lane) is word 64 (DC/2 R + k/2) + 2 lane + (k & 1):
+// the check pass moves two messages per 8-byte access (conflict free), an edge's bank becomes
+// 2 (lane % 16) + (k & 1), and the host search also decides which half of a check's edges sit
+// at odd k.
+template <int MODE, int DC, int COOP, int PAIRED>
 __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
 {
     const LdpcLayout& Y = P.lay;
@@ -73,21 +77,39 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
         for (int it = 0; it < Y.max_iter; it++) {
             // 1. check nodes: round R, lane = the check's bank (an empty seat computes on zeros)
             for (int R = w0; R < nR; R += wstep) {
-                float* base = msg + 32 * DC * R + lane;
-                float out[DC];
-                if (MODE == 1) {
-                    float x[DC];
+                float* base = msg + 32 * DC * R + (PAIRED ? 2 * lane : lane);
+                float x[DC], out[DC];
+                if (PAIRED) {
+#pragma unroll
+                    for (int k = 0; k < DC; k += 2) {
+                        const float2 v = *reinterpret_cast<const float2*>(base + 32 * k);
+                        x[k] = v.x;
+                        x[k + 1] = v.y;
+                    }
+                } else {
 #pragma unroll
                     for (int k = 0; k < DC; k++) x[k] = base[32 * k];
+                }
+                if (MODE == 1) {
                     cn_ms_core<float, DC>(x, out, P.norm);
                 } else {
                     uint32_t xb[DC];
 #pragma unroll
-                    for (int k = 0; k < DC; k++) xb[k] = __float_as_uint(base[32 * k]);
+                    for (int k = 0; k < DC; k++) xb[k] = __float_as_uint(x[k]);
                     cn_bp_core<DC, true, true>(xb, out, DC);
                 }
+                if (PAIRED) {
 #pragma unroll
-                for (int k = 0; k < DC; k++) base[32 * k] = out[k];
+                    for (int k = 0; k < DC; k += 2) {
+                        float2 v;
+                        v.x = out[k];
+                        v.y = out[k + 1];
+                        *reinterpret_cast<float2*>(base + 32 * k) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DC; k++) base[32 * k] = out[k];
+                }
             }
             sync();
             // 2. variable nodes + 3. hard decision, in position space
@@ -119,7 +141,7 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
                     unsigned par = 0;
 #pragma unroll
                     for (int k = 0; k < DC; k++) {
-                        const int cp = P.cpos[32 * (DC * R + k) + lane];
+                        const int cp = P.cpos[PAIRED ? 32 * DC * R + 32 * (k & ~1) + 2 * lane + (k & 1) : 32 * (DC * R + k) + lane];
                         if (cp != 0xffff) par ^= hard[cp >> 5] >> (cp & 31);
                     }
                     bad |= (par & 1u) != 0;

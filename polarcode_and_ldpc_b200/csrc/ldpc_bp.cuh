@@ -34,6 +34,7 @@ struct LdpcLayout {
     int off_msg, off_llr, off_hard, off_ctl, warp_bytes;
     int coop;                   // 1: the whole block decodes one frame (large codes), 0: one warp per frame
     int banked, nR, NP, NS;     // banked layout (ldpc_banked_kernel): check rounds, variable positions, slots
+    int paired;                 // banked layout with two messages of a check per 8-byte word pair
 };
 
 template <typename real>

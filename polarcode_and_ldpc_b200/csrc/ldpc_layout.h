@@ -32,16 +32,38 @@ struct LayoutRng {
 };
 
 // var_checks[v][0..2] ascending, check_vars[c][0..dc-1] ascending
+// paired = true: the k-th message of the check at (R, lane) is word 64 (dc/2 R + k/2) + 2 lane + (k & 1),
+// so a check moves its messages with 8-byte accesses and an edge's bank is 2 (lane % 16) + (k & 1):
+// the search also chooses, per check, which half of its edges sit at odd k.
 static bool build_banked_layout(int m, int n, int dc, const std::vector<int>& var_checks,
-                                const std::vector<int>& check_vars, long budget, BankedLayout* out)
+                                const std::vector<int>& check_vars, long budget, BankedLayout* out, bool paired = false)
 {
     const int nr = (n + 31) / 32, nR = (m + 31) / 32;
+    if (paired && (dc & 1)) return false;
+    // par[c * dc + k]: parity of the seat of the k-th (ascending) variable of check c
+    std::vector<unsigned char> par((size_t)m * dc, 0);
+    if (paired)
+        for (int c = 0; c < m; c++)
+            for (int k = 0; k < dc; k++) par[(size_t)c * dc + k] = (unsigned char)(k & 1);
+    auto edge_k = [&](int c, int v) {
+        int k = 0;
+        while (check_vars[(size_t)c * dc + k] != v) k++;
+        return k;
+    };
+    auto bank_of = [&](int c, int k, int lane) { return paired ? 2 * (lane & 15) + par[(size_t)c * dc + k] : lane; };
     if ((long)32 * dc * nR > 65535 || 32 * nr > 65535) return false;
     std::vector<int> lam(m), rd(n), lamcnt(32, 0), rcnt(nr, 0), C((size_t)nr * 32, 0);
     for (int c = 0; c < m; c++) { lam[c] = c % 32; lamcnt[lam[c]]++; }
     for (int v = 0; v < n; v++) { rd[v] = v / 32; rcnt[rd[v]]++; }
+    // vk[3 v + j]: index of variable v among the variables of its j-th check
+    std::vector<int> vk(3 * (size_t)n);
     for (int v = 0; v < n; v++)
-        for (int j = 0; j < 3; j++) C[(size_t)rd[v] * 32 + lam[var_checks[3 * v + j]]]++;
+        for (int j = 0; j < 3; j++) vk[3 * v + j] = edge_k(var_checks[3 * v + j], v);
+    for (int v = 0; v < n; v++)
+        for (int j = 0; j < 3; j++) {
+            const int c = var_checks[3 * v + j];
+            C[(size_t)rd[v] * 32 + bank_of(c, vk[3 * v + j], lam[c])]++;
+        }
     auto ex = [](int x) { return x > 3 ? x - 3 : 0; };
     long cur = 0;
     for (int x : C) cur += ex(x);
@@ -49,7 +71,25 @@ static bool build_banked_layout(int m, int n, int dc, const std::vector<int>& va
     double T = 0.2;
     const long cool = budget / 130 + 1;
     for (long it = 0; it < budget && cur > 0; it++) {
-        if (rng.next() % 10 < 5) {
+        const unsigned mv = rng.next() % 10;
+        if (paired && mv == 9) {
+            // swap the seat parity of an even-seated and an odd-seated edge of one check
+            const int c = rng.next() % m;
+            int ke = rng.next() % dc, ko = rng.next() % dc;
+            if (par[(size_t)c * dc + ke] != 0 || par[(size_t)c * dc + ko] != 1) continue;
+            const int re = rd[check_vars[(size_t)c * dc + ke]], ro = rd[check_vars[(size_t)c * dc + ko]];
+            const int b0 = 2 * (lam[c] & 15), b1 = b0 + 1;
+            long d = 0;
+            int* cell[4] = {&C[(size_t)re * 32 + b0], &C[(size_t)re * 32 + b1], &C[(size_t)ro * 32 + b1], &C[(size_t)ro * 32 + b0]};
+            const int dv[4] = {-1, 1, -1, 1};
+            for (int t = 0; t < 4; t++) { d += ex(*cell[t] + dv[t]) - ex(*cell[t]); *cell[t] += dv[t]; }
+            if (d <= 0 || rng.u01() < exp(-(double)d / T)) {
+                par[(size_t)c * dc + ke] = 1; par[(size_t)c * dc + ko] = 0;
+                cur += d;
+            } else {
+                for (int t = 0; t < 4; t++) *cell[t] -= dv[t];
+            }
+        } else if (mv < 5) {
             // move a check to another lane (swap with a check of that lane when the lane is full)
             const int a = rng.next() % m, lb = rng.next() % 32, la = lam[a];
             if (la == lb) continue;
@@ -62,8 +102,9 @@ static bool build_banked_layout(int m, int n, int dc, const std::vector<int>& va
             auto shift = [&](int c, int from, int to, int sgn) {
                 for (int k = 0; k < dc; k++) {
                     const int r = rd[check_vars[(size_t)c * dc + k]];
-                    int& x = C[(size_t)r * 32 + from];
-                    int& y = C[(size_t)r * 32 + to];
+                    int& x = C[(size_t)r * 32 + bank_of(c, k, from)];
+                    int& y = C[(size_t)r * 32 + bank_of(c, k, to)];
+                    if (&x == &y) continue;
                     if (sgn > 0) { d += ex(x - 1) - ex(x); x--; d += ex(y + 1) - ex(y); y++; }
                     else { x++; y--; }
                 }
@@ -90,7 +131,7 @@ static bool build_banked_layout(int m, int n, int dc, const std::vector<int>& va
             long d = 0;
             auto shift = [&](int v, int from, int to, int sgn) {
                 for (int j = 0; j < 3; j++) {
-                    const int l = lam[var_checks[3 * v + j]];
+                    const int l = bank_of(var_checks[3 * v + j], vk[3 * v + j], lam[var_checks[3 * v + j]]);
                     int& x = C[(size_t)from * 32 + l];
                     int& y = C[(size_t)to * 32 + l];
                     if (sgn > 0) { d += ex(x - 1) - ex(x); x--; d += ex(y + 1) - ex(y); y++; }
@@ -125,15 +166,26 @@ static bool build_banked_layout(int m, int n, int dc, const std::vector<int>& va
         out->varof[pi] = (uint16_t)v;
         out->posof[v] = (uint16_t)pi;
     }
-    // slot of edge (c, k-th variable of c in ascending order): 32 (dc R + k) + lane
-    auto slot_of = [&](int c, int v) {
-        int k = 0;
-        while (check_vars[(size_t)c * dc + k] != v) k++;
-        return 32 * (dc * seatR[c] + k) + lam[c];
+    // seat index kk of every edge inside its check: ascending variables (paired: the even-parity
+    // edges take kk = 0, 2, .., the odd ones 1, 3, ..); slot = 32 (dc R + kk) + lane, or
+    // 64 (dc/2 R + kk/2) + 2 lane + (kk & 1) in the paired layout
+    std::vector<int> seatk((size_t)m * dc, 0);
+    for (int c = 0; c < m; c++) {
+        int ne = 0, no = 0;
+        for (int k = 0; k < dc; k++) {
+            if (!paired) seatk[(size_t)c * dc + k] = k;
+            else if (par[(size_t)c * dc + k]) seatk[(size_t)c * dc + k] = 2 * (no++) + 1;
+            else seatk[(size_t)c * dc + k] = 2 * (ne++);
+        }
+        if (paired && (ne != dc / 2 || no != dc / 2)) return false;
+    }
+    auto slot_ck = [&](int c, int k) {
+        const int kk = seatk[(size_t)c * dc + k];
+        return paired ? 64 * ((dc / 2) * seatR[c] + (kk >> 1)) + 2 * lam[c] + (kk & 1) : 32 * (dc * seatR[c] + kk) + lam[c];
     };
+    auto slot_of = [&](int c, int v) { return slot_ck(c, edge_k(c, v)); };
     for (int c = 0; c < m; c++)
-        for (int k = 0; k < dc; k++)
-            out->cpos[32 * (dc * seatR[c] + k) + lam[c]] = out->posof[check_vars[(size_t)c * dc + k]];
+        for (int k = 0; k < dc; k++) out->cpos[slot_ck(c, k)] = out->posof[check_vars[(size_t)c * dc + k]];
 
     // per round: which of the three instructions fetches which edge (local search over the 6 orders)
     static const int PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
@@ -145,7 +197,10 @@ static bool build_banked_layout(int m, int n, int dc, const std::vector<int>& va
             if (rd[v] == r) vs.push_back(v);
         int mult[3][32] = {};
         auto add = [&](int v, int pidx, int sgn) {
-            for (int j = 0; j < 3; j++) mult[j][lam[var_checks[3 * v + PERM[pidx][j]]]] += sgn;
+            for (int j = 0; j < 3; j++) {
+                const int jj = PERM[pidx][j], c = var_checks[3 * v + jj];
+                mult[j][bank_of(c, vk[3 * v + jj], lam[c])] += sgn;
+            }
         };
         auto cost = [&]() {
             int cst = 0;

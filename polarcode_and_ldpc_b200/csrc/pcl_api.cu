@@ -482,8 +482,12 @@ static int ldpc_with_kernel_c(pcl_ldpc* h, Fn&& fn)
 {
     if constexpr (sizeof(real) == 4) {
         if (h->lay.banked) {
-            if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, COOP>);
-            return fn(ldpc_banked_kernel<0, 6, COOP>);
+            if (h->lay.paired) {
+                if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, COOP, 1>);
+                return fn(ldpc_banked_kernel<0, 6, COOP, 1>);
+            }
+            if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, COOP, 0>);
+            return fn(ldpc_banked_kernel<0, 6, COOP, 0>);
         }
     }
     if (h->mode == PCL_LDPC_MS) {
@@ -591,15 +595,16 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     Y.nhw = (n + 31) / 32;
     // fp32 production build, regular (3, 6) codes: conflict-free banked layout (ldpc_banked.cuh)
     BankedLayout bl;
-    Y.banked = 0; Y.nR = 0; Y.NP = 0; Y.NS = 0;
+    Y.banked = 0; Y.nR = 0; Y.NP = 0; Y.NS = 0; Y.paired = 0;
     if (h->regular6 && dtype == PCL_F32 && E > 0 && env_int("PCL_LDPC_BANKED", 1) != 0) {
         std::vector<int> var_checks(3 * (size_t)n), check_vars(6 * (size_t)m);
         for (int v = 0; v < n; v++)
             for (int j = 0; j < 3; j++) var_checks[3 * v + j] = vperm[vptr[v] + j] / 6;   // edge e belongs to check e / 6
         for (int e = 0; e < E; e++) check_vars[e] = col[e];
         const long budget = std::min<long>(16000000L, 2700L * E);
-        if (build_banked_layout(m, n, 6, var_checks, check_vars, env_int("PCL_LDPC_ANNEAL", (int)budget), &bl)) {
-            Y.banked = 1; Y.nR = bl.nR; Y.NP = bl.NP; Y.NS = bl.NS;
+        const bool paired = env_int("PCL_LDPC_PAIRED", 1) != 0;
+        if (build_banked_layout(m, n, 6, var_checks, check_vars, env_int("PCL_LDPC_ANNEAL", (int)budget), &bl, paired)) {
+            Y.banked = 1; Y.nR = bl.nR; Y.NP = bl.NP; Y.NS = bl.NS; Y.paired = paired ? 1 : 0;
             h->banked_residual = bl.residual;
         }
     }
