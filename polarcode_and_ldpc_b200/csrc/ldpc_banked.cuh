@@ -13,7 +13,7 @@
 //     the 32 words one instruction touches lie in 32 different banks (bank = l).  (a), (b) come
 //     from a short annealing run at handle creation (a round's 96 edges must hit every bank
 //     exactly 3 times), (c) from recolouring; the few edges that cannot be placed cost one extra
-//     wavefront each (about 11 of the 1512 fetches of a pass for the n = 504 code).
+//     wavefront each (about 10 of the 1512 fetches of a pass for the n = 504 code).
 // Hard decisions, the channel LLRs and the syndrome test live in position space; `varof` /
 // `posof` translate at frame load and store.  The variable sum adds its three messages in
 // instruction order, not in ascending check order, and BP messages are carried in units of ln 2
