@@ -20,6 +20,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #define PCL_VERSION_NUM 100
@@ -603,7 +605,28 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
         for (int e = 0; e < E; e++) check_vars[e] = col[e];
         const long budget = std::min<long>(16000000L, 2700L * E);
         const bool paired = env_int("PCL_LDPC_PAIRED", 1) != 0;
-        if (build_banked_layout(m, n, 6, var_checks, check_vars, env_int("PCL_LDPC_ANNEAL", (int)budget), &bl, paired)) {
+        const long iters = env_int("PCL_LDPC_ANNEAL", (int)budget);
+        // the search is deterministic in (graph, options): keep its result for the next handle of the same code
+        static std::mutex cache_mu;
+        static std::map<unsigned long long, BankedLayout> cache;
+        unsigned long long key = 1469598103934665603ull;
+        auto mix = [&](unsigned long long x) { key = (key ^ x) * 1099511628211ull; };
+        mix((unsigned long long)m); mix((unsigned long long)n); mix(paired ? 1 : 0); mix((unsigned long long)iters);
+        for (int e = 0; e < E; e++) mix(col[e]);
+        bool have = false;
+        {
+            std::lock_guard<std::mutex> lk(cache_mu);
+            auto itc = cache.find(key);
+            if (itc != cache.end()) { bl = itc->second; have = true; }
+        }
+        if (!have) {
+            have = build_banked_layout(m, n, 6, var_checks, check_vars, iters, &bl, paired);
+            if (have) {
+                std::lock_guard<std::mutex> lk(cache_mu);
+                if (cache.size() < 64) cache[key] = bl;
+            }
+        }
+        if (have) {
             Y.banked = 1; Y.nR = bl.nR; Y.NP = bl.NP; Y.NS = bl.NS; Y.paired = paired ? 1 : 0;
             h->banked_residual = bl.residual;
         }
