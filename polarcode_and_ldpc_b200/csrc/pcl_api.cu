@@ -87,6 +87,19 @@ static int device_info(DeviceInfo* di)
 #endif
 }
 
+#ifndef PCL_EMU
+// The small helper kernels (error counters, frame generator) ask for the same shared-memory
+// carve-out as the decoders they run between: an SM that has to change its L1 / shared split
+// between two launches was seen to take the next decode kernel's blocks at the OLD split (fewer
+// resident blocks; the rest of the grid runs as a tail), 8.0 instead of 10.0 Gbps (SCL-8) and 3.6
+// instead of 9.0 Gbps (BP) in bench runs of one binary.  PCL_AUX_CARVEOUT=-1 restores the default.
+static void aux_carveout(const void* kern)
+{
+    const int pct = env_int("PCL_AUX_CARVEOUT", 100);
+    if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+}
+#endif
+
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 static inline int ilog2i(int v) { int n = 0; while ((1 << n) < v) n++; return n; }
 static inline int bit_reverse_i(int v, int nbits)
@@ -920,6 +933,9 @@ extern "C" int pcl_gen_frames_channel(pcl_gen_t* h, int64_t F, int64_t frame0, u
     const int wpb = 4;
     const int grid = (int)std::min<int64_t>((F + wpb - 1) / wpb, 148 * 16);
     const int smem = wpb * h->NW * 4;
+#ifndef PCL_EMU
+    aux_carveout((const void*)framegen_kernel);
+#endif
     PCL_LAUNCH(framegen_kernel, grid, wpb * 32, smem, stream, P);
     CUDA_TRY(cudaGetLastError());
     return PCL_OK;
@@ -982,6 +998,7 @@ extern "C" int pcl_count_errors(const uint8_t* bits_dev, const uint8_t* ref_dev,
     CountArgs a{bits_dev, ref_dev, F, width, ncmp, counters_dev};
     PCL_LAUNCH(count_errors_emu, grid, 256, 0, stream, a);
 #else
+    aux_carveout((const void*)count_errors_kernel);
     count_errors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits_dev, ref_dev, F, width, ncmp, counters_dev);
     CUDA_TRY(cudaGetLastError());
 #endif

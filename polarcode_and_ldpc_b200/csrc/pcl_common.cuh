@@ -73,9 +73,16 @@ template <> struct pcl_math<float> {
     // f(a,b) = sign(a) sign(b) min(|a|,|b|)  (reference: polar/decoder.py:121-127)
     static PCL_DEVICE float f(float a, float b)
     {
+#if defined(PCL_EMU) || defined(PCL_NO_XORSIGN)
         float mn = fminf(fabsf(a), fabsf(b));
         uint32_t s = (__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u;
         return __uint_as_float(__float_as_uint(mn) | s);
+#else
+        // one FMNMX.XORSIGN instead of FMNMX + 2 LOP3: min(|a|,|b|) with sign(a) ^ sign(b), exact
+        float r;
+        asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+        return r;
+#endif
     }
     // log(1 + exp(-|x|)), the sign-independent part of decoder.py:374-406
     static PCL_DEVICE float softplus_neg_abs(float ax) { return log1pf(expf(-ax)); }

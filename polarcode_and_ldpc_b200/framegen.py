@@ -26,28 +26,36 @@ from . import _native
 class FrameGenerator:
     """generate(F, snr_db, ...) -> (llr[F, N], message[F, K] uint8, codeword[F, N] uint8) on the device."""
 
-    def __init__(self, handle, N: int, K: int, kind: str):
-        self._h, self.N, self.K, self.kind = handle, N, K, kind
+    def __init__(self, handle, N: int, K: int, kind: str, device=None):
+        self._h, self.N, self.K, self.kind, self.device = handle, N, K, kind, device
+
+    @staticmethod
+    def _device(device):
+        torch = _native.require_cuda()
+        return torch, (torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device))
 
     @classmethod
-    def polar(cls, N: int, K: int, frozen_bits) -> "FrameGenerator":
-        """Frames of PolarEncoder(N, K, frozen_bits) (src/polar/encoder.py:20-95, no CRC)."""
-        _native.require_cuda()
+    def polar(cls, N: int, K: int, frozen_bits, device=None) -> "FrameGenerator":
+        """Frames of PolarEncoder(N, K, frozen_bits) (src/polar/encoder.py:20-95, no CRC).  The code
+        tables live on `device` (default: the current CUDA device); generate() runs there."""
+        torch, device = cls._device(device)
         mask = np.zeros(N, dtype=np.uint8)
         mask[np.asarray(frozen_bits, dtype=np.int64)] = 1
         h = ctypes.c_void_p()
-        _native.check(_native.lib().pcl_gen_polar_create(ctypes.byref(h), N, K, ctypes.c_void_p(mask.ctypes.data)))
-        return cls(h, N, K, "polar")
+        with torch.cuda.device(device):
+            _native.check(_native.lib().pcl_gen_polar_create(ctypes.byref(h), N, K, ctypes.c_void_p(mask.ctypes.data)))
+        return cls(h, N, K, "polar", device)
 
     @classmethod
-    def ldpc(cls, G) -> "FrameGenerator":
+    def ldpc(cls, G, device=None) -> "FrameGenerator":
         """Frames of LDPCEncoder(G=G): codeword = message @ G mod 2 (src/ldpc/encoder.py:88-90); G is [k, n]."""
-        _native.require_cuda()
+        torch, device = cls._device(device)
         G = np.ascontiguousarray(np.asarray(G) % 2, dtype=np.uint8)
         k, n = G.shape
         h = ctypes.c_void_p()
-        _native.check(_native.lib().pcl_gen_ldpc_create(ctypes.byref(h), n, k, ctypes.c_void_p(G.ctypes.data)))
-        return cls(h, n, k, "ldpc")
+        with torch.cuda.device(device):
+            _native.check(_native.lib().pcl_gen_ldpc_create(ctypes.byref(h), n, k, ctypes.c_void_p(G.ctypes.data)))
+        return cls(h, n, k, "ldpc", device)
 
     CHANNELS = {"awgn": 0, "rayleigh": 1, "bsc": 2}
 
@@ -57,7 +65,10 @@ class FrameGenerator:
         channel knowledge) or "bsc" (BSCChannel(crossover_prob=snr_db): the second argument is then
         the crossover probability and the LLRs are +-ln((1 - p) / p))."""
         torch = _native.require_cuda()
-        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        device = self.device if device is None else torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        assert device == self.device, f"generator tables live on {self.device}, generate() was asked for {device}"
         code = _native.dtype_code(dtype)
         tdt = torch.float64 if code == _native.PCL_F64 else torch.float32
         llr = torch.empty((F, self.N), dtype=tdt, device=device)

@@ -75,3 +75,38 @@ def generator_from_parity(H: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     # pivot row i reads: x[pivots[i]] = sum_j A[i, free_j] x[free_j]
     G[:, pivots] = A[:len(pivots)][:, free].T
     return G.astype(np.int64), free
+
+
+# ---- the reference's helper names (src/ldpc/matrix.py, src/ldpc/utils.py), inputs only -----
+def mackay_construction(n: int, k: int, dv: int, dc: int, seed: Optional[int] = None) -> np.ndarray:
+    """Reference name of mackay_parity_check (/root/reference/src/ldpc/matrix.py:12)."""
+    return mackay_parity_check(n, k, dv, dc, seed)
+
+
+def generate_ldpc_matrix(n: int, k: int, method: str = "mackay", dv: int = 3, dc: int = 6,
+                         seed: Optional[int] = None) -> np.ndarray:
+    """H[m, n], m = n - k (/root/reference/src/ldpc/matrix.py:53-91): "mackay" re-derives dc from
+    dv n / m when the degrees do not balance, "random" draws iid bits from the legacy RNG."""
+    m = n - k
+    if method == "mackay":
+        if dv * n != dc * m:
+            dc = (dv * n) // m
+        return mackay_parity_check(n, k, dv, dc, seed)
+    if method == "random":
+        if seed is not None:
+            np.random.seed(seed)
+        return np.random.randint(0, 2, (m, n))
+    raise ValueError(f"Unknown method: {method}")
+
+
+def create_tanner_graph(H: np.ndarray):
+    """(var_neighbors, check_neighbors) adjacency lists, ascending (/root/reference/src/ldpc/utils.py:11-34)."""
+    H = np.asarray(H)
+    check_neighbors = [np.flatnonzero(row == 1).tolist() for row in H]
+    var_neighbors = [np.flatnonzero(col == 1).tolist() for col in H.T]
+    return var_neighbors, check_neighbors
+
+
+def check_syndrome(H: np.ndarray, codeword: np.ndarray) -> bool:
+    """H c^T == 0 over GF(2) (/root/reference/src/ldpc/utils.py:37-49)."""
+    return bool(np.all((np.asarray(H) @ np.asarray(codeword)) % 2 == 0))

@@ -24,10 +24,19 @@ class LDPCEncoder:
         self.m = self.H.shape[0]
         if G is not None:
             G = np.asarray(G)
-            self.G = G.T if G.shape[0] == n and G.shape[1] != n else G
+            # pyldpc hands back (n, k); the reference accepts either orientation and nothing else (encoder.py:57-63)
+            if G.shape == (n, k) and n != k:
+                self.G = G.T
+            elif G.shape == (k, n):
+                self.G = G
+            else:
+                raise ValueError(f"G shape {G.shape} doesn't match (n,k)={n, k} or (k,n)={k, n}")
             self.info_positions = np.arange(self.G.shape[0])
         else:
             self.G, self.info_positions = generator_from_parity(self.H)
+        # k is the true dimension of the code: equal to the caller's k for a supplied G, and
+        # n - rank(H) when G comes from H (the reference keeps the nominal k there, documented difference)
+        self.k_nominal = k
         self.k = self.G.shape[0]
 
     def encode(self, message: np.ndarray) -> np.ndarray:
@@ -37,3 +46,15 @@ class LDPCEncoder:
         messages = np.asarray(messages)
         assert messages.ndim == 2 and messages.shape[1] == self.k, f"Message length must be {self.k}"
         return ((messages.astype(np.int64) @ self.G) % 2).astype(np.int64)
+
+    def verify_codeword(self, codeword: np.ndarray) -> bool:
+        return bool(np.all((self.H @ np.asarray(codeword)) % 2 == 0))
+
+    def get_code_rate(self) -> float:
+        return self.k / self.n
+
+    def get_parity_check_matrix(self) -> np.ndarray:
+        return self.H.copy()
+
+    def __repr__(self) -> str:
+        return f"LDPCEncoder(n={self.n}, k={self.k}, rate={self.get_code_rate():.3f})"

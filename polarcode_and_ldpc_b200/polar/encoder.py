@@ -31,6 +31,7 @@ class PolarEncoder:
             self.frozen_bits = np.asarray(frozen_bits)
             self.info_bits = np.setdiff1d(np.arange(N), self.frozen_bits)
             assert len(self.info_bits) == K, "Number of info bits must equal K"
+        self.frozen_values = np.zeros(len(self.frozen_bits), dtype=int)      # encoder.py:61
 
     def encode(self, message: np.ndarray) -> np.ndarray:
         return self.encode_batch(np.asarray(message)[None, :])[0]
@@ -46,5 +47,14 @@ class PolarEncoder:
         u[:, self.info_bits] = messages
         return polar_transform(u).astype(np.int64)
 
+    def get_info_bits_positions(self) -> np.ndarray:
+        return self.info_bits.copy()
+
+    def get_frozen_bits_positions(self) -> np.ndarray:
+        return self.frozen_bits.copy()
+
     def get_code_rate(self) -> float:
         return self.K / self.N
+
+    def __repr__(self) -> str:
+        return f"PolarEncoder(N={self.N}, K={self.K}" + (f", CRC={self.crc_polynomial})" if self.use_crc else ")")

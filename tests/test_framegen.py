@@ -60,7 +60,7 @@ def test_emu_polar_and_ldpc_frames():
         H = P.gallager_parity_check(n, 3, 6, 42)
         G, _ = P.generator_from_parity(H)
         llr, msg, cw = emu.gen_frames("ldpc", n, G.shape[0], G, 40, 0.5, seed=5, dtype="f64")
-        _check_frames("ldpc", n, G.shape[0], G, P.LDPCEncoder(n, n // 2, H=H, G=G), llr, msg, cw, 0.5, 1e-3)
+        _check_frames("ldpc", n, G.shape[0], G, P.LDPCEncoder(n, G.shape[0], H=H, G=G), llr, msg, cw, 0.5, 1e-3)
         assert not ((H @ cw.T.astype(np.int64)) % 2).any()
 
 
@@ -138,7 +138,7 @@ def test_gpu_framegen_matches_host_encoders_and_statistics():
         G, _ = P.generator_from_parity(H)
         gen = P.FrameGenerator.ldpc(G)
         llr, msg, cw = gen.generate(2048, 1.0, seed=3, dtype="float64")
-        _check_frames("ldpc", n, G.shape[0], G, P.LDPCEncoder(n, n // 2, H=H, G=G), llr.cpu().numpy(),
+        _check_frames("ldpc", n, G.shape[0], G, P.LDPCEncoder(n, G.shape[0], H=H, G=G), llr.cpu().numpy(),
                       msg.cpu().numpy(), cw.cpu().numpy(), 1.0, 1e-4)
     from scipy import stats
     gen = P.FrameGenerator.polar(1024, 512, P.bhattacharyya_frozen_set(1024, 512, 2.0))
