@@ -125,6 +125,9 @@ struct pcl_polar {
     int fast = 0;               // register-resident tree bottom (polar_scl_fast.cuh)
     int fpw = 1;                // fast kernel: frames per warp
     int NL = 0, GL = 0;         // fast kernel: compiled-in log2 N and G (0: run-time values)
+    int TM = 0;                 // fast kernel, TM variant: one block per SM, mid levels in tensor / shared memory
+    unsigned long long* d_next[PCL_NSTAGE] = {};   // TM variant: ticket counters (one per host-pipeline stage)
+    unsigned long long tickets[PCL_NSTAGE] = {};   // their current values (never reset: no memset between launches)
     // host-buffer pipeline
     void* d_llr[PCL_NSTAGE] = {};
     uint8_t* d_bits[PCL_NSTAGE] = {};
@@ -137,8 +140,28 @@ struct pcl_polar {
 static size_t real_size(int dtype) { return dtype == PCL_F64 ? 8 : 4; }
 
 static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int rsz, bool crc, bool fast = false,
-                         int fpw = 1)
+                         int fpw = 1, bool tm = false)
 {
+    Y.hdr_bytes = 0;
+    if (tm) {
+        // TM variant (polar_scl_fast.cuh): levels 2 .. n-7 in the global scratch, n-6 and n-4 in tensor
+        // memory, n-5 (32 elements per column) in shared memory; the final u words reuse that region.
+        const int cols = 32;
+        Y.N = N; Y.n = ilog2i(N); Y.K = K; Y.L = L; Y.G = Y.n - 7;
+        Y.NW = N / 32; Y.nb = Y.n - 5;
+        Y.uw_slots = crc ? cols : fpw;
+        Y.hdr_bytes = 128;
+        int off = 0;
+        Y.off_cm = off;     off += fpw * pcl_fast_frame_bytes(LP);
+        Y.off_newpm = off;
+        Y.off_llr = off;    off += std::max(cols * 32 * rsz, Y.uw_slots * Y.NW * 4);
+        Y.off_uw = Y.off_llr;                      // written after the last level walk of a frame
+        Y.off_sel = off;
+        Y.off_bw = off;     off += cols * (N / 32 - 1) * 4;
+        Y.warp_bytes = align_up(off, 16);
+        Y.scratch_per_warp = (int64_t)cols * ((N >> 2) - (N >> Y.G));      // levels 3 .. n-7 (1 and 2 are never stored)
+        return;
+    }
     // `cols` = (frame, slot) columns a warp carries: LP for the generic kernel, LP * fpw for the fast one
     const int cols = LP * fpw;
     Y.N = N; Y.n = ilog2i(N); Y.K = K; Y.L = L; Y.G = G;
@@ -171,20 +194,21 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
 // owns a path, 32 / LP frames per warp (polar_scl_fast.cuh); X(LP, log2 N, G) with log2 N = 0
 // for the run-time code length, else the code length and G compiled in as constants.
 #ifdef PCL_QUICK   // experiment builds (scripts/build_variants.py): headline kernels only
-#define PCL_POLAR_FAST_VARIANTS(X) X(8, 0, 0) X(8, 10, 5)
+#define PCL_POLAR_FAST_VARIANTS(X) X(8, 0, 0, 0) X(8, 10, 5, 0) X(8, 10, 3, 1)
 #else
 #define PCL_POLAR_FAST_VARIANTS(X) \
-    X(1, 0, 0) X(2, 0, 0) X(4, 0, 0) X(8, 0, 0) X(16, 0, 0) X(32, 0, 0) \
-    X(8, 7, 1) X(8, 8, 2) X(8, 9, 4) X(8, 10, 5) X(8, 11, 7) X(8, 12, 8) X(32, 10, 5) X(1, 8, 2)
+    X(1, 0, 0, 0) X(2, 0, 0, 0) X(4, 0, 0, 0) X(8, 0, 0, 0) X(16, 0, 0, 0) X(32, 0, 0, 0) \
+    X(8, 7, 1, 0) X(8, 8, 2, 0) X(8, 9, 4, 0) X(8, 10, 5, 0) X(8, 11, 7, 0) X(8, 12, 8, 0) X(32, 10, 5, 0) X(1, 8, 2, 0) \
+    X(8, 10, 3, 1)
 #endif
 // (SCL-8 gains 1.2-1.9 x from a compiled code length at every N = 128 .. 4096.  SC, LP = 1, does
 // not in general -- N = 1024: 29 Gbps compiled vs 40 at run time; with no prune its time is all
 // level walk and the unrolled walk is bigger code -- so only the N = 256 quick-start size of
 // BASELINE configs[0] keeps one: 47 vs 41 Gbps at the bench's batch of 524 288 frames.)
 
-static bool polar_fast_variant_exists(int LP, int nl, int gl)
+static bool polar_fast_variant_exists(int LP, int nl, int gl, int tm = 0)
 {
-#define X(lp, n_, g_) if (LP == lp && nl == n_ && gl == g_) return true;
+#define X(lp, n_, g_, tm_) if (LP == lp && nl == n_ && gl == g_ && tm == tm_) return true;
     PCL_POLAR_FAST_VARIANTS(X)
 #undef X
     return false;
@@ -194,9 +218,10 @@ template <typename real, typename Fn>
 static int polar_with_kernel(pcl_polar* h, Fn&& fn)
 {
     if (h->fast) {
-#define X(lp, n_, g_)                                                                          \
+#define X(lp, n_, g_, tm_)                                                                     \
     if constexpr (n_ == 0 || sizeof(real) == 4) {                                                   \
-        if (h->LP == lp && h->NL == n_ && h->GL == g_) return fn(polar_scl_fast_kernel<lp, real, n_, g_>); \
+        if (h->LP == lp && h->NL == n_ && h->GL == g_ && h->TM == tm_)                              \
+            return fn(polar_scl_fast_kernel<lp, real, n_, g_, tm_>);                                \
     }
         PCL_POLAR_FAST_VARIANTS(X)
 #undef X
@@ -285,45 +310,76 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     int rc = device_info(&di);
     if (rc) { delete h; return rc; }
     const int rsz = (int)real_size(dtype);
-    h->wpb = env_int("PCL_POLAR_WPB", 4);
-    if (h->wpb < 1 || h->wpb > 4) h->wpb = 4;
-    // Fast kernel: tree bottom in registers; needs N >= 16 and the packed 32-bit slot
-    // pointers to hold (n-4) LLR-level fields and (n-5) left-level fields of log2(LP) bits.
     int pb = 0;
     while ((1 << pb) < LP) pb++;
-    h->fast = (n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 &&
-               env_int("PCL_POLAR_GENERIC", 0) == 0) ? 1 : 0;
-    // a lane owns a whole path, 32 / LP frames share a warp's instruction stream (measured best
-    // on B200 for L = 8: 3.7 Gbps vs 2.9 / 2.0 with 2 / 4 lanes per path, profiles/r01d, r01e)
-    h->fpw = h->fast ? 32 / LP : 1;
-    const int gmax = h->fast ? n - 4 : n - 1;
-    int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 8192 : 9216);
-    int G = env_int("PCL_POLAR_G", -1);
-    const int gmin = h->fast ? 1 : 0;
-    if (G < 0) {
-        for (G = gmin; G < gmax; G++) {
-            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
-            if (h->lay.warp_bytes <= budget) break;
-        }
-    }
-    if (G > gmax) G = gmax;
-    if (G < gmin) G = gmin;
-    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
-    h->NL = 0; h->GL = 0;
-    // code lengths with log2 N and G compiled in (fp32 build; the validation build reads them at run time)
-    if (h->fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && polar_fast_variant_exists(LP, n, G)) { h->NL = n; h->GL = G; }
-    h->smem_bytes = h->lay.warp_bytes * h->wpb;
-    if (h->smem_bytes > di.smem_per_block) {
-        delete h;
-        return fail(PCL_EUNSUPPORTED, "shared memory %d B per block exceeds the device limit", h->smem_bytes);
-    }
+    // Kernel choice.  (1) fast kernel (tree bottom in registers): needs N >= 16 and the packed 32-bit slot
+    // pointers to hold (n-4) LLR-level fields and (n-5) left-level fields of log2(LP) bits; (2) its TM
+    // variant (one block per SM, mid levels in tensor / shared memory) where one is compiled; (3) the
+    // generic all-shared-memory kernel.  A configuration whose shared memory does not fit a block retries
+    // with fewer warps per block (4, 2, 1) and then falls back to the next kernel in the list.
+    const bool can_fast = n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 && env_int("PCL_POLAR_GENERIC", 0) == 0;
+    const bool can_tm = can_fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && env_int("PCL_POLAR_TM", 1) != 0 &&
+                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1);
     int bps = 1;
-#ifndef PCL_EMU
-    rc = (dtype == PCL_F64) ? polar_occ<double>(h, h->wpb * 32, h->smem_bytes, &bps)
-                            : polar_occ<float>(h, h->wpb * 32, h->smem_bytes, &bps);
-    if (rc) { delete h; return rc; }
-    if (bps < 1) { delete h; return fail(PCL_ECUDA, "kernel does not fit on an SM"); }
+    bool placed = false;
+    for (int attempt = can_tm ? 0 : (can_fast ? 1 : 2); attempt < 3 && !placed; attempt++) {
+        h->TM = attempt == 0;
+        h->fast = attempt <= 1;
+        if (attempt == 1 && !can_fast) continue;
+        // a lane owns a whole path, 32 / LP frames share a warp's instruction stream (measured best
+        // on B200 for L = 8: 3.7 Gbps vs 2.9 / 2.0 with 2 / 4 lanes per path, profiles/r01d, r01e)
+        h->fpw = h->fast ? 32 / LP : 1;
+        h->NL = 0; h->GL = 0;
+        if (h->TM) {
+            polar_layout(h->lay, N, K, list_size, LP, n - 7, rsz, crc_len > 0, true, h->fpw, true);
+            h->NL = n; h->GL = n - 7;
+#ifdef PCL_EMU
+            int w = env_int("PCL_POLAR_WPB", 8);       // two groups are enough to exercise the tickets
+#else
+            int w = env_int("PCL_POLAR_WPB", PCL_POLAR_TM_THREADS / 32);
 #endif
+            w = std::max(4, std::min(w, PCL_POLAR_TM_THREADS / 32)) & ~3;
+            while (w > 4 && h->lay.hdr_bytes + h->lay.warp_bytes * w > di.smem_per_block) w -= 4;
+            h->wpb = w;
+            h->smem_bytes = h->lay.hdr_bytes + h->lay.warp_bytes * w;
+            if (h->smem_bytes > di.smem_per_block) continue;
+        } else {
+            const int gmax = h->fast ? n - 4 : n - 1;
+            const int budget = env_int("PCL_POLAR_SMEM_PER_WARP", h->fast ? 8192 : 9216);
+            int G = env_int("PCL_POLAR_G", -1);
+            const int gmin = h->fast ? 1 : 0;
+            if (G < 0) {
+                for (G = gmin; G < gmax; G++) {
+                    polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
+                    if (h->lay.warp_bytes <= budget) break;
+                }
+            }
+            G = std::max(gmin, std::min(G, gmax));
+            polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
+            // code lengths with log2 N and G compiled in (fp32 build; the validation build reads them at run time)
+            if (h->fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && polar_fast_variant_exists(LP, n, G, 0)) { h->NL = n; h->GL = G; }
+            int w = env_int("PCL_POLAR_WPB", 4);
+            if (w < 1 || w > 4) w = 4;
+            while (w > 1 && h->lay.warp_bytes * w > di.smem_per_block) w >>= 1;
+            h->wpb = w;
+            h->smem_bytes = h->lay.warp_bytes * w;
+            if (h->smem_bytes > di.smem_per_block) continue;
+        }
+        bps = 1;
+#ifndef PCL_EMU
+        rc = (dtype == PCL_F64) ? polar_occ<double>(h, h->wpb * 32, h->smem_bytes, &bps)
+                                : polar_occ<float>(h, h->wpb * 32, h->smem_bytes, &bps);
+        if (rc) { delete h; return rc; }
+        if (bps < 1) continue;
+#endif
+        placed = true;
+    }
+    if (!placed) {
+        const int need = h->smem_bytes;
+        delete h;
+        return fail(PCL_EUNSUPPORTED, "no kernel configuration fits: shared memory %d B per block against the device limit %d B",
+                    need, di.smem_per_block);
+    }
     {
         const int cap = env_int("PCL_POLAR_BPS", 0);     // experiment knob: resident blocks per SM
         if (cap > 0 && cap < bps) bps = cap;
@@ -340,6 +396,12 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
         cudaMemcpy(h->d_info_pos, ip.data(), (size_t)K * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
         pcl_polar_destroy(h);
         return fail(PCL_ECUDA, "cudaMemcpy failed (tables)");
+    }
+    if (h->TM) {
+        if (cudaMalloc((void**)&h->d_next[0], 8) != cudaSuccess || cudaMemset(h->d_next[0], 0, 8) != cudaSuccess) {
+            pcl_polar_destroy(h);
+            return fail(PCL_ECUDA, "cudaMalloc failed (ticket counter)");
+        }
     }
     if (h->scratch_bytes) {
         if (cudaMalloc(&h->d_scratch[0], h->scratch_bytes) != cudaSuccess) {
@@ -358,6 +420,7 @@ extern "C" void pcl_polar_destroy(pcl_polar_t* h)
     cudaFree(h->d_info_pos);
     for (int s = 0; s < PCL_NSTAGE; s++) {
         cudaFree(h->d_scratch[s]);
+        cudaFree(h->d_next[s]);
         cudaFree(h->d_llr[s]);
         cudaFree(h->d_bits[s]);
 #ifndef PCL_EMU
@@ -373,7 +436,7 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
                                      int* fast)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
-    if (fast) *fast = h->fast ? (h->NL ? 2 : 1) : 0;
+    if (fast) *fast = h->fast ? (h->TM ? 3 : (h->NL ? 2 : 1)) : 0;
     if (grid) *grid = h->last_grid;
     if (block) *block = h->wpb * 32;
     if (smem_bytes) *smem_bytes = h->smem_bytes;
@@ -383,7 +446,7 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
 
 template <typename real>
 static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8_t* bits_dev, double* pm_dev,
-                             void* leaf_dev, uint8_t* parent_dev, void* scratch, void* stream)
+                             void* leaf_dev, uint8_t* parent_dev, void* scratch, void* stream, int stage = 0)
 {
     PolarParams<real> P;
     P.lay = h->lay;
@@ -403,6 +466,17 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
     const int64_t fpb = (int64_t)h->wpb * h->fpw;            // frames per block per pass
     int64_t need = (F + fpb - 1) / fpb;
     int grid = (int)std::min<int64_t>(need, h->grid_max);
+    P.next = nullptr;
+    P.ticket_base = 0;
+    if (h->TM) {
+        // groups of 4 warps pull chunks of 4 fpw frames; a small batch spreads its chunks over the SMs
+        const int64_t chunks = (F + 4 * h->fpw - 1) / (4 * h->fpw);
+        grid = (int)std::min<int64_t>(chunks, h->grid_max);
+        P.next = h->d_next[stage];
+        P.ticket_base = h->tickets[stage];
+        // every group fetches until it draws a ticket past the end: chunks + one per group
+        h->tickets[stage] += (unsigned long long)chunks + (unsigned long long)grid * (h->wpb / 4);
+    }
     h->last_grid = grid;
     int rc = polar_launch<real>(h, P, grid, stream);
     if (rc) return rc;
@@ -445,6 +519,11 @@ extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64
     for (int s = 0; s < PCL_NSTAGE; s++) {
         if (!h->st[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->st[s], cudaStreamNonBlocking));
         if (!h->d_scratch[s] && h->scratch_bytes) CUDA_TRY(cudaMalloc(&h->d_scratch[s], h->scratch_bytes));
+        if (h->TM && !h->d_next[s]) {
+            CUDA_TRY(cudaMalloc((void**)&h->d_next[s], 8));
+            CUDA_TRY(cudaMemset(h->d_next[s], 0, 8));
+            h->tickets[s] = 0;
+        }
     }
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     int stage = 0;
@@ -454,8 +533,8 @@ extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64
         CUDA_TRY(cudaMemcpyAsync(h->d_llr[stage], (const char*)llr_host + (size_t)f0 * h->N * rsz,
                                  (size_t)fc * h->N * rsz, cudaMemcpyHostToDevice, st));
         int rc = (h->dtype == PCL_F64)
-            ? polar_decode_impl<double>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st)
-            : polar_decode_impl<float>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st);
+            ? polar_decode_impl<double>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st, stage)
+            : polar_decode_impl<float>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st, stage);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(bits_host + (size_t)f0 * h->K, h->d_bits[stage], (size_t)fc * h->K,
                                  cudaMemcpyDeviceToHost, st));
@@ -677,8 +756,9 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
     }
     h->smem_bytes = Y.coop ? Y.warp_bytes : Y.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
+        const int need = Y.warp_bytes;           // Y lives inside *h
         delete h;
-        return fail(PCL_EUNSUPPORTED, "code too large: %d B of shared memory per frame", Y.warp_bytes);
+        return fail(PCL_EUNSUPPORTED, "code too large: %d B of shared memory per frame", need);
     }
     int bps = 1;
 #ifndef PCL_EMU

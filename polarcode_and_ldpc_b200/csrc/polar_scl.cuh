@@ -48,6 +48,7 @@ struct PolarLayout {
     // per-warp shared memory byte offsets
     int off_cm, off_newpm, off_sel, off_llr, off_bw, off_uw, warp_bytes;
     int uw_slots;        // 1, or LP when CRC selection needs every path's u
+    int hdr_bytes;       // TM variant: per-block header (TMEM base, group tickets) ahead of the warps' regions
     int64_t scratch_per_warp;  // reals of global scratch per resident warp
 };
 
@@ -63,6 +64,8 @@ struct PolarParams {
     const uint16_t* info_pos;      // [K] decode step of the k-th info bit
     real* scratch;                 // global scratch for levels 1..G
     int64_t F;
+    unsigned long long* next;      // TM variant: ticket counter the groups of warps pull frame chunks from
+    unsigned long long ticket_base;  // value of *next when this launch started (the counter is never reset)
     int want_pm;                   // L == 1: maintain the metric only when asked
     int use_crc, crc_len;
     uint32_t crc_poly;

@@ -40,6 +40,7 @@
 // u = 2^(-|x| log2 e) (one ex2, one rcp, 6 FMA; |error| < 1e-7).
 #pragma once
 #include "pcl_common.cuh"
+#include "pcl_tmem.cuh"
 #include "polar_scl.cuh"
 
 // ---- fast softplus(-|x|) ------------------------------------------------------------
@@ -329,6 +330,199 @@ PCL_DEVICE void pcl_level2_vec(real* dst, const real* y, int n, const uint32_t* 
     }
 }
 
+
+// Level 3 of one path straight from the channel LLRs: neither level 1 nor level 2 is ever stored
+// (TM variant).  Element k of level 3 comes from the EIGHT consecutive channel values at
+// 8 br(k): pairs (0,1) (2,3) (4,5) (6,7) are level-1 elements k, k + 2s, k + s, k + 3s (s = N/8), the
+// first two and the last two pairs make level-2 elements k and k + s.  Quad i4 = br(t) of level 3
+// needs the 32-byte groups at 8 (t + mm N/32), mm = 0 .. 3: iteration t walks four sequential streams.
+// The 8 (or 32) lanes of a frame need the same 128 bytes per iteration, so every lane fetches ONE
+// 16-byte piece with cp.async into a ring in shared memory (the region of the levels that this very
+// walk recomputes afterwards) and all lanes read the pieces back as broadcasts: an eighth of the
+// global loads, DEPTH rounds in flight, no registers held across the wait.
+template <int LP, bool BIT1, bool BIT2, bool BIT3>
+PCL_DEVICE void pcl_level3_fused(float* dst, const float* yf, int n, float* stage, int lane,
+                                 const uint32_t* b1, const uint32_t* b2, const uint32_t* b3)
+{
+    static_assert(LP >= 8, "a frame needs at least 8 lanes to fetch its 8 pieces");
+    constexpr int R = LP / 8;                     // iterations one round of 32 pieces covers
+    constexpr int DEPTH = 8;                      // rounds in the ring (8 x 512 bytes)
+    const int nq3 = 1 << (n - 5);                 // quads of level 3
+    const int sz3 = 4 * nq3;
+    const int nrounds = nq3 / R;
+    const int piece = lane & 7, grp8 = lane >> 3;
+    const int sub = (lane & (LP - 1)) >> 3;       // which iteration of the round this lane fetches for
+    const int fr = lane / LP;
+    const float* src0 = yf + 8 * (sub + (piece >> 1) * nq3) + 4 * (piece & 1);
+    float* mine = stage + grp8 * 32 + piece * 4;
+#pragma unroll 1
+    for (int rr = 0; rr < DEPTH - 1; rr++) {
+        if (rr < nrounds) pcl_cp_async16(mine + rr * 128, src0 + 8 * R * rr);
+        pcl_cp_async_commit();
+    }
+#pragma unroll 1
+    for (int rr = 0; rr < nrounds; rr++) {
+        pcl_cp_async_wait<DEPTH - 2>();           // this lane's piece of round rr has landed ...
+        __syncwarp();                             // ... and so have the others'; round rr - 1 is consumed
+        const int nx = rr + DEPTH - 1;
+        if (nx < nrounds) pcl_cp_async16(mine + (nx % DEPTH) * 128, src0 + 8 * R * nx);
+        pcl_cp_async_commit();
+#pragma unroll
+        for (int su = 0; su < R; su++) {
+            const int t = rr * R + su;
+            const float* sp = stage + (rr % DEPTH) * 128 + (fr * R + su) * 32;
+            const int i4 = (int)(__brev((unsigned)t) >> (37 - n));          // (n-5)-bit reversal
+            const int k4 = 4 * i4;
+            const int sh = k4 & 31;
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, l0 = 0, l1 = 0, t0 = 0;
+            if (BIT1) {
+                m0 = b1[(k4 >> 5) * 32] >> sh;
+                m1 = b1[((k4 + sz3) >> 5) * 32] >> sh;
+                m2 = b1[((k4 + 2 * sz3) >> 5) * 32] >> sh;
+                m3 = b1[((k4 + 3 * sz3) >> 5) * 32] >> sh;
+            }
+            if (BIT2) {
+                l0 = b2[(k4 >> 5) * 32] >> sh;
+                l1 = b2[((k4 + sz3) >> 5) * 32] >> sh;
+            }
+            if (BIT3) t0 = b3[(k4 >> 5) * 32] >> sh;
+            float out[4];
+#pragma unroll
+            for (int mm = 0; mm < 4; mm++) {
+                const int r = ((mm & 1) << 1) | (mm >> 1);                  // 2-bit reversal
+                float v[8];
+                pcl_load_quad<float>(sp + 8 * mm, v);
+                pcl_load_quad<float>(sp + 8 * mm + 4, v + 4);
+                float p01, p23, p45, p67;
+                if (BIT1) {
+                    p01 = pcl_fast<float>::gs(v[0], v[1], m0 << (31 - r));
+                    p23 = pcl_fast<float>::gs(v[2], v[3], m2 << (31 - r));
+                    p45 = pcl_fast<float>::gs(v[4], v[5], m1 << (31 - r));
+                    p67 = pcl_fast<float>::gs(v[6], v[7], m3 << (31 - r));
+                } else {
+                    p01 = pcl_math<float>::f(v[0], v[1]);
+                    p23 = pcl_math<float>::f(v[2], v[3]);
+                    p45 = pcl_math<float>::f(v[4], v[5]);
+                    p67 = pcl_math<float>::f(v[6], v[7]);
+                }
+                const float q0 = BIT2 ? pcl_fast<float>::gs(p01, p23, l0 << (31 - r)) : pcl_math<float>::f(p01, p23);
+                const float q1 = BIT2 ? pcl_fast<float>::gs(p45, p67, l1 << (31 - r)) : pcl_math<float>::f(p45, p67);
+                out[r] = BIT3 ? pcl_fast<float>::gs(q0, q1, t0 << (31 - r)) : pcl_math<float>::f(q0, q1);
+            }
+            pcl_stq<true, float>(dst + i4 * 128, out);
+        }
+    }
+    pcl_cp_async_wait<0>();
+    __syncwarp();                                 // the ring region goes back to the level that owns it
+}
+
+// ---- TM variant (fp32, compiled code length, n >= 9): the three levels below the global scratch
+// stay on chip.  Level n-6 (64 elements per path) and level n-4 (16) live in TENSOR MEMORY, one
+// TMEM lane per path (pcl_tmem.cuh); level n-5 (32) in shared memory.  A path always writes its own
+// lane; a path that has to read another slot's array (the first level of a walk after a prune
+// moved it) lets every lane load its own array and fetches the values with shuffles.
+template <bool BIT>
+PCL_DEVICE void pcl_level_g2t(uint32_t tdst, const float* src, const uint32_t* bsrc)
+{
+    constexpr int nq = 16;                        // destination quads; source quads i and i + 16
+    float a[2][4], b[2][4], a2[2][4], b2[2][4];
+    uint32_t wb = 0;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        pcl_ldq<true, float>(src + u * 128, a[u]);
+        pcl_ldq<true, float>(src + (u + nq) * 128, b[u]);
+    }
+#pragma unroll 2
+    for (int i = 0; i < nq; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            pcl_ldq<true, float>(src + (i + 2 + u) * 128, a2[u]);
+            pcl_ldq<true, float>(src + (i + 2 + u + nq) * 128, b2[u]);
+        }
+        if (BIT && (i & 7) == 0) wb = bsrc[(i >> 3) * 32];
+        const uint32_t w4 = wb >> (4 * (i & 7));
+        {
+            float out[8];
+            uint32_t o[8];
+#pragma unroll
+            for (int u = 0; u < 2; u++) pcl_quad_op<BIT, float>(out + 4 * u, a[u], b[u], w4 >> (4 * u));
+#pragma unroll
+            for (int k = 0; k < 8; k++) o[k] = __float_as_uint(out[k]);
+            pcl_tmem_st<8>(tdst + 4 * i, o);
+        }
+        if (i + 4 < nq) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                pcl_ldq<true, float>(src + (i + 4 + u) * 128, a[u]);
+                pcl_ldq<true, float>(src + (i + 4 + u + nq) * 128, b[u]);
+            }
+        }
+        {
+            float out[8];
+            uint32_t o[8];
+#pragma unroll
+            for (int u = 0; u < 2; u++) pcl_quad_op<BIT, float>(out + 4 * u, a2[u], b2[u], w4 >> (8 + 4 * u));
+#pragma unroll
+            for (int k = 0; k < 8; k++) o[k] = __float_as_uint(out[k]);
+            pcl_tmem_st<8>(tdst + 4 * i + 8, o);
+        }
+    }
+    pcl_tmem_wait_st();
+}
+
+// level n-5 (32 elements, shared memory, own column) from level n-6 in tensor memory
+template <bool BIT>
+PCL_DEVICE void pcl_level_t2s(float* dst, uint32_t tsrc, int srcl, bool ident, uint32_t wb)
+{
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        uint32_t a[8], b[8];
+        pcl_tmem_ld<8>(tsrc + 8 * h, a);
+        pcl_tmem_ld<8>(tsrc + 32 + 8 * h, b);
+        pcl_tmem_wait_ld();
+        if (!ident) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                a[k] = __shfl_sync(PCL_FULL_MASK, a[k], srcl);
+                b[k] = __shfl_sync(PCL_FULL_MASK, b[k], srcl);
+            }
+        }
+#pragma unroll
+        for (int qd = 0; qd < 2; qd++) {
+            float fa[4], fb[4], out[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                fa[e] = __uint_as_float(a[4 * qd + e]);
+                fb[e] = __uint_as_float(b[4 * qd + e]);
+            }
+            pcl_quad_op<BIT, float>(out, fa, fb, wb >> (8 * h + 4 * qd));
+            pcl_store_quad<float>(dst + (2 * h + qd) * 128, out);
+        }
+    }
+}
+
+// level n-4 (16 elements, tensor memory) from level n-5 in shared memory (column of the source slot)
+template <bool BIT>
+PCL_DEVICE void pcl_level_s2t(uint32_t tdst, const float* src, uint32_t smf)
+{
+    float a[4][4], b[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        pcl_load_quad<float>(src + u * 128, a[u]);
+        pcl_load_quad<float>(src + (u + 4) * 128, b[u]);
+    }
+    uint32_t o[16];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        float out[4];
+        pcl_quad_op<BIT, float>(out, a[u], b[u], smf >> (4 * u));
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[4 * u + e] = __float_as_uint(out[e]);
+    }
+    pcl_tmem_st<16>(tdst, o);
+    pcl_tmem_wait_st();
+}
+
 // LP = list slots per frame (power of two); a warp decodes FPW = 32 / LP frames side by side.
 // NL = log2 N as a compile-time constant (0: read it from the layout), GL = G for that NL.
 #ifndef PCL_PRUNE_SHORTCUT
@@ -340,9 +534,14 @@ PCL_DEVICE void pcl_level2_vec(real* dst, const real* y, int n, const uint32_t* 
 #ifndef PCL_POLAR_MINB
 #define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for (80 regs)
 #endif
-template <int LP, typename real, int NL, int GL>
-__global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3) polar_scl_fast_kernel(PolarParams<real> P)
+#ifndef PCL_POLAR_TM_THREADS
+#define PCL_POLAR_TM_THREADS 640   // TM variant: ONE block per SM, 20 warps = 5 groups of 4 (96 registers; 768 / 80 is 7 % slower)
+#endif
+template <int LP, typename real, int NL, int GL, int TM = 0>
+__global__ void __launch_bounds__(TM ? PCL_POLAR_TM_THREADS : 128, TM ? 1 : ((sizeof(real) == 4) ? PCL_POLAR_MINB : 3))
+polar_scl_fast_kernel(PolarParams<real> P)
 {
+    static_assert(!TM || (NL >= 9 && GL == NL - 7 && sizeof(real) == 4), "TM variant: fp32, compiled code length >= 512");
     constexpr int PB = pcl_log2<LP>::v;
     constexpr int FPW = 32 / LP;                 // frames per warp
     constexpr int NC = 2 * LP;                   // prune candidates per frame
@@ -364,7 +563,7 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
     const int shift = (N < 32) ? 32 - N : 0;
     const int NB = N >> 3;
 
-    unsigned char* wsm = pcl_dyn_smem() + (size_t)warp * Y.warp_bytes;
+    unsigned char* wsm = pcl_dyn_smem() + (TM ? Y.hdr_bytes : 0) + (size_t)warp * Y.warp_bytes;
     unsigned char* fb = wsm + Y.off_cm + fr * FB; // this frame's prune scratch
     double* cm = (double*)fb;                     // candidate keys: 2p -> bit 0, 2p + 1 -> bit 1 of path p
     double* newpm = (double*)(fb + NC * 8);       // survivor keys (fp32 build) / metrics, by rank
@@ -376,17 +575,45 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
 
     const double DEAD = -1.0e300;                 // metric of an inactive slot (sorts last, stays finite)
 
+    // TM variant: one block per SM owns the SM's tensor memory; warp w works in lane quarter w % 4,
+    // columns (w / 4) * TMW .. : level n-6 at +0 (64 columns), level n-4 at +64 (16 columns).
+    // Groups of 4 warps pull chunks of 4 FPW frames from a ticket counter and meet at their own
+    // named barrier (the whole-block barrier of the other variant would couple all 24 warps).
+    uint32_t tL4 = 0, tL6 = 0;
+    const int grp = warp >> 2, gw = warp & 3;
+    uint32_t* hdr = (uint32_t*)pcl_dyn_smem();    // [0] TMEM base, [4 + 4 g + 2 k ..] ticket of group g, parity k (64 bit)
+    if (TM) {
+        if (warp == 0) pcl_tmem_alloc_all(hdr);
+        pcl_tmem_fence_before();
+        __syncthreads();
+        pcl_tmem_fence_after();
+        const int tmw = (PCL_TMEM_COLS / ((wpb + 3) >> 2)) & ~15;
+        tL4 = pcl_tmem_addr(hdr[0], warp, grp * tmw);
+        tL6 = tL4 + 64;
+    }
+
     // Every warp of a block makes the same number of passes (a pass past the end of the batch
     // works on masked-off frames) and the block meets at a barrier before each pass: all frames
     // follow the same instruction stream, so warps that start together stay close to the same
     // tree position and share their instruction working set (measured +3 %; barriers inside the
     // pass, every 1 .. 64 blocks of 8 leaves, gain less the more often they come).
-    for (int64_t fb = (int64_t)blockIdx.x * wpb * FPW; fb < P.F; fb += (int64_t)gridDim.x * wpb * FPW) {
-        __syncthreads();
-        const int64_t f0 = fb + (int64_t)warp * FPW;
+    int64_t fbase = (int64_t)blockIdx.x * wpb * FPW;
+    for (int pass = 0;; pass++) {
+        if (TM) {
+            unsigned long long* tk = (unsigned long long*)(hdr + 4) + 2 * grp + (pass & 1);
+            if (gw == 0 && lane == 0) *tk = atomicAdd(P.next, 1ull) - P.ticket_base;
+            pcl_named_barrier(1 + grp, 128);
+            fbase = (int64_t)(*(volatile unsigned long long*)tk) * (4 * FPW);
+            if (fbase >= P.F) break;
+        } else {
+            if (pass) fbase += (int64_t)gridDim.x * wpb * FPW;
+            if (fbase >= P.F) break;
+            __syncthreads();
+        }
+        const int64_t f0 = fbase + (int64_t)(TM ? gw : warp) * FPW;
         const int64_t f = f0 + fr;
         const bool valid = f < P.F;
-        const real* y = P.llr + (valid ? f : fb) * N;
+        const real* y = P.llr + (valid ? f : fbase) * N;
         int nact = 1;
         bool act = (p == 0) && valid;
         double pm = act ? 0.0 : DEAD;
@@ -404,7 +631,96 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
 #pragma unroll
             for (int t = 0; t < 8; t++) R3[t] = (real)0;
             const int bit3 = (i0 >> 3) & 1;       // f or g at level n-3
-            if (n >= 6) {
+            if constexpr (TM != 0) {
+                const int start = (blk == 0) ? 2 : n - (__ffs(i0) - 1);     // <= n-3
+                // Levels 1 and 2 are never stored: level 3 comes straight from the channel LLRs, every
+                // lane of the warp fetching a share of them (pcl_level3_fused); global level d >= 3 of
+                // the scratch sits at 32 (N/4 - N >> (d-1)).
+                if (start <= 3) {
+                    const int bit1 = (i0 >> (n - 1)) & 1, bit2 = (i0 >> (n - 2)) & 1, bit3l = (i0 >> (n - 3)) & 1;
+                    const uint32_t* b1src = bw + cbase + (ptrB & (LP - 1));
+                    const uint32_t* b2src = bw + 32 * ((N >> 5) - (N >> 6)) + cbase + ((ptrB >> PB) & (LP - 1));
+                    const uint32_t* b3src = bw + 32 * ((N >> 5) - (N >> 7)) + cbase + ((ptrB >> (2 * PB)) & (LP - 1));
+                    float* dst = (float*)gl + 4 * lane;
+                    float* ring = (float*)sl;
+                    const float* yf = (const float*)y;
+                    switch (bit1 * 4 + bit2 * 2 + bit3l) {
+                        case 0: pcl_level3_fused<LP, false, false, false>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        case 1: pcl_level3_fused<LP, false, false, true>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        case 2: pcl_level3_fused<LP, false, true, false>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        case 3: pcl_level3_fused<LP, false, true, true>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        case 4: pcl_level3_fused<LP, true, false, false>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        case 5: pcl_level3_fused<LP, true, false, true>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        case 6: pcl_level3_fused<LP, true, true, false>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                        default: pcl_level3_fused<LP, true, true, true>(dst, yf, n, ring, lane, b1src, b2src, b3src); break;
+                    }
+                    ptrL = (ptrL & ~((uint32_t)(LP - 1) << (2 * PB))) | ((uint32_t)p << (2 * PB));
+                }
+#pragma unroll
+                for (int d = 4; d <= n - 7; d++) {                          // global scratch -> global scratch
+                    if (d >= start && act) {
+                        const int nq = (N >> d) >> 2;
+                        const int bit = (i0 >> (n - d)) & 1;
+                        const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
+                        const uint32_t* bsrc = bw + 32 * ((N >> 5) - (N >> (d + 4))) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
+                        const real* src = gl + 32 * ((N >> 2) - (N >> (d - 2))) + 4 * (cbase + q);
+                        real* dst = gl + 32 * ((N >> 2) - (N >> (d - 1))) + 4 * lane;
+                        if (bit) pcl_level_vec<true, true, true, real>(dst, src, nq, bsrc, 0u);
+                        else pcl_level_vec<false, true, true, real>(dst, src, nq, bsrc, 0u);
+                        ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                    }
+                }
+                // The on-chip levels run on every lane of the warp: tcgen05.ld / st are warp-wide, an
+                // inactive lane computes on whatever its slot holds and nobody ever reads its result.
+                if (n - 6 >= start) {                                       // level n-6: global -> tensor memory
+                    constexpr int d = NL - 6;
+                    const int bit = (i0 >> (n - d)) & 1;
+                    const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
+                    const uint32_t* bsrc = bw + 32 * ((N >> 5) - (N >> (d + 4))) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1));
+                    const float* src = (const float*)gl + 32 * ((N >> 2) - (N >> (d - 2))) + 4 * (cbase + q);
+                    if (bit) pcl_level_g2t<true>(tL4, src, bsrc);
+                    else pcl_level_g2t<false>(tL4, src, bsrc);
+                    ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                }
+                if (n - 5 >= start) {                                       // level n-5: tensor memory -> shared memory
+                    constexpr int d = NL - 5;
+                    const int bit = (i0 >> (n - d)) & 1;
+                    const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
+                    const bool ident = __all_sync(PCL_FULL_MASK, !act || q == p);
+                    const uint32_t wb = bw[32 * ((N >> 5) - (N >> (d + 4))) + cbase + ((ptrB >> ((d - 1) * PB)) & (LP - 1))];
+                    if (bit) pcl_level_t2s<true>((float*)sl + 4 * lane, tL4, cbase + q, ident, wb);
+                    else pcl_level_t2s<false>((float*)sl + 4 * lane, tL4, cbase + q, ident, 0u);
+                    ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                }
+                if (n - 4 >= start) {                                       // level n-4: shared memory -> tensor memory
+                    constexpr int d = NL - 4;
+                    const int bit = (i0 >> (n - d)) & 1;
+                    const int q = (ptrL >> ((d - 2) * PB)) & (LP - 1);
+                    const float* src = (const float*)sl + 4 * (cbase + q);
+                    if (bit) pcl_level_s2t<true>(tL6, src, small);
+                    else pcl_level_s2t<false>(tL6, src, small);
+                    ptrL = (ptrL & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                }
+                {                                                           // level n-3 (registers) from level n-4
+                    const int q = (ptrL >> ((n - 5) * PB)) & (LP - 1);
+                    const bool ident = __all_sync(PCL_FULL_MASK, !act || q == p);
+                    uint32_t v[16];
+                    pcl_tmem_ld<16>(tL6, v);
+                    pcl_tmem_wait_ld();
+                    if (!ident) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) v[k] = __shfl_sync(PCL_FULL_MASK, v[k], cbase + q);
+                    }
+                    if (bit3) {
+#pragma unroll
+                        for (int t = 0; t < 8; t++)
+                            R3[t] = (real)pcl_fast<float>::gs(__uint_as_float(v[t]), __uint_as_float(v[t + 8]), small << (15 - t));
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 8; t++) R3[t] = (real)pcl_math<float>::f(__uint_as_float(v[t]), __uint_as_float(v[t + 8]));
+                    }
+                }
+            } else if (n >= 6) {
                 const int start = (blk == 0) ? 2 : n - (__ffs(i0) - 1);     // <= n-3
                 const uint32_t* b1src = bw + cbase + (ptrB & (LP - 1));     // left array of level 1
                 if (start <= 2) {
@@ -838,5 +1154,10 @@ __global__ void __launch_bounds__(128, (sizeof(real) == 4) ? PCL_POLAR_MINB : 3)
             }
         }
         __syncwarp();
+    }
+    if (TM) {
+        pcl_tmem_fence_before();
+        __syncthreads();
+        if (warp == 0) pcl_tmem_free_all(hdr[0]);
     }
 }

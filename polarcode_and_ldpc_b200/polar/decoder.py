@@ -118,7 +118,7 @@ class _PolarBase:
                 "kernel": "polar_scl_fast_kernel" if fa.value else "polar_scl_kernel",
                 "lanes_per_path": 1 if fa.value else 32 // self._LP,
                 "frames_per_warp": (32 // self._LP) if fa.value else 1,
-                "compiled_code_length": fa.value == 2}
+                "compiled_code_length": fa.value >= 2, "tensor_memory": fa.value == 3}
 
     def decode_batch_host(self, llr_host, bits_host=None):
         """C-ABI host-buffer path: llr_host is a CPU tensor/array [F, N] in the compute

@@ -49,8 +49,9 @@ struct Fiber {
     std::vector<char> stack;
     bool done = false;
     bool started = false;
-    int wait_kind = 0;  // 0 runnable, 1 warp barrier, 2 block barrier
+    int wait_kind = 0;  // 0 runnable, 1 warp barrier, 2 block barrier, 3 named barrier
     unsigned wait_gen = 0;
+    int wait_id = 0;
 };
 
 struct WarpState {
@@ -70,6 +71,9 @@ struct BlockState {
     int current = -1;
     std::function<void()> body;
     std::vector<unsigned char> smem;
+    std::vector<uint32_t> tmem;                 // tensor memory: 128 lanes x 512 columns (pcl_tmem.cuh)
+    struct NamedBar { unsigned gen = 0; int arrived = 0; };
+    NamedBar named[16];
 };
 
 inline BlockState*& cur_block() { static BlockState* b = nullptr; return b; }
@@ -105,6 +109,39 @@ inline void block_barrier() {
     f.wait_kind = 2; f.wait_gen = b->block_gen;
     while (b->block_gen == f.wait_gen) yield_to_sched();
     f.wait_kind = 0;
+}
+
+// bar.sync id, nthreads: the first `nthreads` arrivals release the barrier
+inline void named_barrier(int id, int nthreads) {
+    BlockState* b = cur_block();
+    int t = b->current;
+    BlockState::NamedBar& nb = b->named[id & 15];
+    nb.arrived++;
+    if (nb.arrived >= nthreads) { nb.arrived = 0; nb.gen++; return; }
+    Fiber& f = b->fibers[t];
+    unsigned g = nb.gen;
+    f.wait_kind = 3; f.wait_gen = g; f.wait_id = id & 15;
+    while (b->named[id & 15].gen == g) yield_to_sched();
+    f.wait_kind = 0;
+}
+
+// tcgen05.ld / st, shape 32x32b.xN: lane l of warp w moves N consecutive columns of TMEM lane
+// 32 (w % 4) + l; the lane field of the address must name the warp's own quarter
+inline void tmem_access(uint32_t taddr, uint32_t* v, int nx, bool store) {
+    BlockState* b = cur_block();
+    int t = b->current;
+    if (b->tmem.empty()) b->tmem.assign(128 * 512, 0xCDCDCDCDu);
+    int lane_field = (int)(taddr >> 16), col = (int)(taddr & 0xffffu);
+    int quarter = ((t / 32) & 3) * 32;
+    if (lane_field != quarter || col < 0 || col + nx > 512) {
+        fprintf(stderr, "simt_emu: bad TMEM access (lane field %d, warp quarter %d, col %d x%d)\n", lane_field, quarter, col, nx);
+        abort();
+    }
+    uint32_t* row = b->tmem.data() + (size_t)(quarter + t % 32) * 512 + col;
+    for (int k = 0; k < nx; k++) {
+        if (store) row[k] = v[k];
+        else v[k] = row[k];
+    }
 }
 
 inline void fiber_entry() {
@@ -154,6 +191,7 @@ inline void run_block(unsigned bx, dim3 grid, dim3 block, size_t smem_bytes, con
             if (f.done) continue;
             if (f.wait_kind == 1 && bs.warps[t / 32].gen == f.wait_gen) continue;
             if (f.wait_kind == 2 && bs.block_gen == f.wait_gen) continue;
+            if (f.wait_kind == 3 && bs.named[f.wait_id].gen == f.wait_gen) continue;
             bs.current = t;
             tidx() = {(unsigned)t, 0, 0};
             swapcontext(&bs.sched, &f.ctx);
