@@ -367,30 +367,47 @@ def run_gpu_workload(name, steps, warmup, env, snr=None, frames=None, with_e2e=F
 
     # ---- end to end through the C-ABI host-buffer call --------------------------
     if with_e2e:
+        width = kbits if w["kind"] == "polar" else w["n"]
+        words = (width + 31) // 32
+        shifts = torch.arange(32, device=device, dtype=torch.int32)
+
+        def e2e_leg(llr_host, label):
+            bits_host = torch.empty((F, words), dtype=torch.int32, pin_memory=True)
+            dec.decode_batch_host(llr_host, bits_host, packed=True)
+            dec.decode_batch_host(llr_host, bits_host, packed=True)
+            times = []
+            barrier()
+            t_all = time.perf_counter()
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                dec.decode_batch_host(llr_host, bits_host, packed=True)   # synchronous: returns with the bits on the host
+                times.append(time.perf_counter() - t0)
+            torch.cuda.synchronize()
+            el = torch.tensor([float(np.median(times)), time.perf_counter() - t_all], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            # unpack a slice on the device and compare with the transmitted bits
+            sl = bits_host[:4096].to(device)
+            got = ((sl.unsqueeze(-1) >> shifts) & 1).reshape(sl.shape[0], -1)[:, :ref.shape[1]].to(torch.uint8)
+            ok = bool((got == ref[:4096]).all(dim=1).float().mean() > 0.5)
+            return {"value": world * F * kbits / float(el[0]) / 1e9, "unit": "Gbps",
+                    "h2d_bytes_per_step": int(llr_host.numel() * llr_host.element_size()),
+                    "d2h_bytes_per_step": int(bits_host.numel() * 4),
+                    "value_mean_of_steps": world * F * kbits * steps / float(el[1]) / 1e9,
+                    "api": f"pcl_*_decode_host_ex (C ABI): pinned {label} LLRs in, bit-packed rows out (packed on the device)",
+                    "sane": ok}
+
         llr_host = torch.empty(llr.shape, dtype=llr.dtype, pin_memory=True)
         llr_host.copy_(llr)
-        width = kbits if w["kind"] == "polar" else w["n"]
-        bits_host = torch.empty((F, width), dtype=torch.uint8, pin_memory=True)
-        dec.decode_batch_host(llr_host, bits_host)
-        dec.decode_batch_host(llr_host, bits_host)
-        times = []
-        barrier()
-        t_all = time.perf_counter()
-        for _ in range(steps):
-            t0 = time.perf_counter()
-            dec.decode_batch_host(llr_host, bits_host)     # synchronous: returns with bits on host
-            times.append(time.perf_counter() - t0)
-        torch.cuda.synchronize()
-        el = torch.tensor([float(np.median(times)), time.perf_counter() - t_all], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        ok = bool((bits_host.to(device)[:, :ref.shape[1]] == ref).all(dim=1).float().mean() > 0.5)
-        res["e2e"] = {"value": world * F * kbits / float(el[0]) / 1e9, "unit": "Gbps",
-                      "h2d_bytes_per_step": int(llr_host.numel() * llr_host.element_size()),
-                      "d2h_bytes_per_step": int(bits_host.numel()),
-                      "value_mean_of_steps": world * F * kbits * steps / float(el[1]) / 1e9,
-                      "api": "pcl_*_decode_host (C ABI, pinned host buffers)", "sane": ok}
-        del llr_host, bits_host
+        res["e2e"] = e2e_leg(llr_host, "float32" if llr.dtype == torch.float32 else "float64")
+        if llr.dtype == torch.float32:
+            # opt-in transport format: half the PCIe bytes, the decoder sees fp16-rounded LLRs (reported
+            # separately; parity of this mode is judged against the oracle fed the same rounded values)
+            llr16 = torch.empty(llr.shape, dtype=torch.float16, pin_memory=True)
+            llr16.copy_(llr)
+            res["e2e_fp16_transport"] = e2e_leg(llr16, "float16")
+            del llr16
+        del llr_host
     if with_dropin:
         # the reference call shape: decode_batch(np.float64[F, N]) from pageable memory, int64 bits back
         Fd = min(F, 32768)
@@ -664,10 +681,12 @@ def main():
         }
         if "per_rank_ms_kernel" in main_res:
             line["per_rank_ms_kernel"] = main_res["per_rank_ms_kernel"]
-        if "e2e_dropin" in main_res or any("e2e_dropin" in r for r in sweep):
-            line["e2e_dropin"] = next(r["e2e_dropin"] for r in (sweep or [main_res]) if "e2e_dropin" in r)
+        for key in ("e2e_dropin", "e2e_fp16_transport"):
+            hit = [r[key] for r in (sweep or [main_res]) if key in r]
+            if hit:
+                line[key] = min(hit, key=lambda e: e["value"])
         keep = ("workload", "desc", "snr_db", "gbps", "ms_per_step", "ms_step", "ms_kernel", "frames_per_s", "e2e",
-                "e2e_dropin", "fer", "roofline", "launch", "frames_per_gpu_per_step", "cpu_baseline", "dtype",
+                "e2e_dropin", "e2e_fp16_transport", "fer", "roofline", "launch", "frames_per_gpu_per_step", "cpu_baseline", "dtype",
                 "per_rank_ms_kernel")
         if sweep:
             line["snr_sweep"] = [{k: r[k] for k in ("snr_db", "gbps", "ms_step", "ms_kernel", "fer", "ber") if k in r} |

@@ -33,6 +33,11 @@ extern "C" {
 
 #define PCL_F32 0         /* production compute type */
 #define PCL_F64 1         /* validation build: bit-exact decoded bits vs the reference */
+#define PCL_F16 2         /* TRANSPORT format of host LLRs only (half the PCIe bytes); widened to fp32 on the device */
+
+#define PCL_OUT_BYTES 0   /* uint8 [F][W], one byte per bit */
+#define PCL_OUT_PACKED 1  /* uint32 [F][ceil(W/32)], bit k of a row at word k / 32, bit k % 32 (packed on the device) */
+#define PCL_OUT_INT64 2   /* int64 [F][W]: what F calls of the reference's decode() return (np.int64) */
 
 #define PCL_LDPC_BP 0     /* BPDecoder  (src/ldpc/decoder.py:11)  */
 #define PCL_LDPC_MS 1     /* MSDecoder  (src/ldpc/decoder.py:208) */
@@ -71,11 +76,23 @@ int pcl_polar_decode_batch(pcl_polar_t* h, const void* llr_dev, int64_t F, uint8
 /* Same call with HOST buffers: chunks the batch, overlaps H2D / decode / D2H. */
 int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
                           void* stream);
+/*
+ * The reference call shape end to end: decode(llr) takes any float array (np.float64 in every
+ * caller, src/polar/decoder.py:47) and returns np.int64[K] (:70-71).  llr_host [F][N] in
+ * `llr_dtype` -- PCL_F64 from pageable memory is narrowed to fp32 by host threads into pinned
+ * staging (fp32 handles; a float64 handle copies it as is), PCL_F32 is copied directly, PCL_F16 is
+ * an opt-in transport format widened on the device -- and out_host in `out_format`
+ * (PCL_OUT_BYTES / PCL_OUT_PACKED / PCL_OUT_INT64).  Chunked; conversion, H2D, decode, D2H and
+ * unpacking of different chunks overlap.
+ */
+int pcl_polar_decode_host_ex(pcl_polar_t* h, const void* llr_host, int llr_dtype, int64_t F, void* out_host,
+                             int out_format, void* stream);
 int pcl_polar_lp(const pcl_polar_t* h);
 /* Launch geometry of the last decode (for gpu_launches / occupancy reporting): grid, block,
  * dynamic shared memory, number of tree levels kept in the L2 scratch, and the kernel in use:
  * 0 = generic kernel, 1 = register-resident-bottom kernel (a lane owns a path, 32 / LP frames
- * per warp), 2 = the same with log2 N and the level split compiled in as constants. */
+ * per warp), 2 = the same with log2 N and the level split compiled in as constants, 3 = the
+ * one-block-per-SM variant with the mid tree levels in tensor / shared memory. */
 int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
                           int* fast);
 
@@ -98,6 +115,10 @@ int pcl_ldpc_decode_batch(pcl_ldpc_t* h, const void* llr_dev, int64_t F, uint8_t
                           int32_t* iters_dev, void* total_dev, void* stream);
 int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
                          int32_t* iters_host, void* stream);
+/* Host-buffer call with the input / output formats of pcl_polar_decode_host_ex (BPDecoder.decode,
+ * src/ldpc/decoder.py:124: float64 in, np.int64[n] out). */
+int pcl_ldpc_decode_host_ex(pcl_ldpc_t* h, const void* llr_host, int llr_dtype, int64_t F, void* out_host,
+                            int out_format, int32_t* iters_host, void* stream);
 int pcl_ldpc_num_edges(const pcl_ldpc_t* h);
 int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, int* smem_bytes);
 /* Shared-memory layout in use: *banked = 1 for the conflict-free layout of regular (3, 6) codes in

@@ -8,7 +8,8 @@ import os
 from . import _build
 
 PCL_OK, PCL_EINVAL, PCL_ECUDA, PCL_EUNSUPPORTED, PCL_EDEGREE1 = 0, 1, 2, 3, 4
-PCL_F32, PCL_F64 = 0, 1
+PCL_F32, PCL_F64, PCL_F16 = 0, 1, 2
+PCL_OUT_BYTES, PCL_OUT_PACKED, PCL_OUT_INT64 = 0, 1, 2
 PCL_LDPC_BP, PCL_LDPC_MS = 0, 1
 
 _lib = None
@@ -43,6 +44,8 @@ def lib() -> ctypes.CDLL:
     L.pcl_polar_destroy.restype = None
     L.pcl_polar_decode_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     L.pcl_polar_decode_host.argtypes = [vp, vp, i64, vp, vp]
+    L.pcl_polar_decode_host_ex.argtypes = [vp, vp, i32, i64, vp, i32, vp]
+    L.pcl_ldpc_decode_host_ex.argtypes = [vp, vp, i32, i64, vp, i32, vp, vp]
     L.pcl_polar_lp.argtypes = [vp]
     L.pcl_polar_launch_info.argtypes = [vp] + [ctypes.POINTER(i32)] * 5
     L.pcl_ldpc_create.argtypes = [ctypes.POINTER(vp), i32, i32, vp, i32, ctypes.c_double, i32, i32, i32]
@@ -68,7 +71,8 @@ def lib() -> ctypes.CDLL:
 
 EXPORTS = [
     "pcl_version", "pcl_last_error", "pcl_device_count",
-    "pcl_polar_create", "pcl_polar_destroy", "pcl_polar_decode_batch", "pcl_polar_decode_host",
+    "pcl_polar_create", "pcl_polar_destroy", "pcl_polar_decode_batch", "pcl_polar_decode_host", "pcl_polar_decode_host_ex",
+    "pcl_ldpc_decode_host_ex",
     "pcl_polar_lp", "pcl_polar_launch_info",
     "pcl_ldpc_create", "pcl_ldpc_destroy", "pcl_ldpc_decode_batch", "pcl_ldpc_decode_host",
     "pcl_ldpc_num_edges", "pcl_ldpc_launch_info", "pcl_ldpc_layout_info", "pcl_count_errors",
@@ -109,3 +113,16 @@ def dtype_code(dtype) -> int:
 
 def default_dtype() -> str:
     return os.environ.get("PCL_DTYPE", "float32")
+
+
+def host_llr(llr, handle_code: int):
+    """numpy LLRs -> (contiguous array, PCL dtype code) for the host-buffer calls: float64 and float32
+    go through as they are (the library narrows float64 for an fp32 handle), anything else is read
+    as float64 like the reference does (np.asarray(llr, dtype=np.float64), decoder.py:47)."""
+    import numpy as np
+    a = np.asarray(llr)
+    if a.dtype == np.float32 and handle_code == PCL_F32:
+        return np.ascontiguousarray(a), PCL_F32
+    if a.dtype == np.float16 and handle_code == PCL_F32:
+        return np.ascontiguousarray(a), PCL_F16
+    return np.ascontiguousarray(a, dtype=np.float64), PCL_F64

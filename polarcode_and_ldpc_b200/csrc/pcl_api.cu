@@ -13,6 +13,7 @@
 #include "ldpc_layout.h"
 #include "ldpc_bp.cuh"
 #include "../../include/pcl.h"
+#include "pcl_host_pipe.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -128,12 +129,8 @@ struct pcl_polar {
     int TM = 0;                 // fast kernel, TM variant: one block per SM, mid levels in tensor / shared memory
     unsigned long long* d_next[PCL_NSTAGE] = {};   // TM variant: ticket counters (one per host-pipeline stage)
     unsigned long long tickets[PCL_NSTAGE] = {};   // their current values (never reset: no memset between launches)
-    // host-buffer pipeline
-    void* d_llr[PCL_NSTAGE] = {};
-    uint8_t* d_bits[PCL_NSTAGE] = {};
-    int64_t chunk = 0;
 #ifndef PCL_EMU
-    cudaStream_t st[PCL_NSTAGE] = {};
+    HostPipe pipe;              // host-buffer pipeline (pcl_host_pipe.cuh)
 #endif
 };
 
@@ -421,12 +418,10 @@ extern "C" void pcl_polar_destroy(pcl_polar_t* h)
     for (int s = 0; s < PCL_NSTAGE; s++) {
         cudaFree(h->d_scratch[s]);
         cudaFree(h->d_next[s]);
-        cudaFree(h->d_llr[s]);
-        cudaFree(h->d_bits[s]);
-#ifndef PCL_EMU
-        if (h->st[s]) cudaStreamDestroy(h->st[s]);
-#endif
     }
+#ifndef PCL_EMU
+    h->pipe.destroy();
+#endif
     delete h;
 }
 
@@ -496,28 +491,17 @@ extern "C" int pcl_polar_decode_batch(pcl_polar_t* h, const void* llr_dev, int64
     return polar_decode_impl<float>(h, llr_dev, F, bits_dev, pm_dev, leaf_dev, parent_dev, h->d_scratch[0], stream);
 }
 
-extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8_t* bits_host, void* stream)
+extern "C" int pcl_polar_decode_host_ex(pcl_polar_t* h, const void* llr_host, int llr_dtype, int64_t F, void* out_host,
+                                        int out_format, void* stream)
 {
     if (!h || F < 0) return fail(PCL_EINVAL, "bad handle or F");
     if (F == 0) return PCL_OK;
-    if (!llr_host || !bits_host) return fail(PCL_EINVAL, "null buffer");
+    if (!llr_host || !out_host) return fail(PCL_EINVAL, "null buffer");
 #ifdef PCL_EMU
-    (void)stream;
+    (void)stream; (void)llr_dtype; (void)out_format;
     return fail(PCL_ECUDA, "no CUDA device");
 #else
-    const size_t rsz = real_size(h->dtype);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 8192)));
-    if (h->chunk < chunk) {
-        for (int s = 0; s < PCL_NSTAGE; s++) {
-            cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]);
-            h->d_llr[s] = nullptr; h->d_bits[s] = nullptr;
-            CUDA_TRY(cudaMalloc(&h->d_llr[s], (size_t)chunk * h->N * rsz));
-            CUDA_TRY(cudaMalloc((void**)&h->d_bits[s], (size_t)chunk * h->K));
-        }
-        h->chunk = chunk;
-    }
     for (int s = 0; s < PCL_NSTAGE; s++) {
-        if (!h->st[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->st[s], cudaStreamNonBlocking));
         if (!h->d_scratch[s] && h->scratch_bytes) CUDA_TRY(cudaMalloc(&h->d_scratch[s], h->scratch_bytes));
         if (h->TM && !h->d_next[s]) {
             CUDA_TRY(cudaMalloc((void**)&h->d_next[s], 8));
@@ -525,23 +509,25 @@ extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64
             h->tickets[s] = 0;
         }
     }
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    int stage = 0;
-    for (int64_t f0 = 0; f0 < F; f0 += chunk, stage = (stage + 1) % PCL_NSTAGE) {
-        const int64_t fc = std::min<int64_t>(chunk, F - f0);
-        cudaStream_t st = h->st[stage];
-        CUDA_TRY(cudaMemcpyAsync(h->d_llr[stage], (const char*)llr_host + (size_t)f0 * h->N * rsz,
-                                 (size_t)fc * h->N * rsz, cudaMemcpyHostToDevice, st));
-        int rc = (h->dtype == PCL_F64)
-            ? polar_decode_impl<double>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st, stage)
-            : polar_decode_impl<float>(h, h->d_llr[stage], fc, h->d_bits[stage], nullptr, nullptr, nullptr, h->d_scratch[stage], st, stage);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(bits_host + (size_t)f0 * h->K, h->d_bits[stage], (size_t)fc * h->K,
-                                 cudaMemcpyDeviceToHost, st));
-    }
-    for (int s = 0; s < PCL_NSTAGE; s++) CUDA_TRY(cudaStreamSynchronize(h->st[s]));
-    return PCL_OK;
+    // a chunk fills the resident grid at least once and carries >= 32 MiB of LLRs
+    const int64_t resident = (int64_t)h->grid_max * h->wpb * h->fpw;
+    int64_t chunk = std::max<int64_t>(resident, ((int64_t)32 << 20) / ((int64_t)h->N * 4));
+    chunk = (chunk + 255) / 256 * 256;
+    chunk = env_int("PCL_HOST_CHUNK", (int)std::min<int64_t>(chunk, 1 << 20));
+    PipeLaunch launch = [h](int stage, cudaStream_t st, const void* d_llr, int64_t fc, uint8_t* d_bits, int32_t*) -> int {
+        return (h->dtype == PCL_F64)
+            ? polar_decode_impl<double>(h, d_llr, fc, d_bits, nullptr, nullptr, nullptr, h->d_scratch[stage], st, stage)
+            : polar_decode_impl<float>(h, d_llr, fc, d_bits, nullptr, nullptr, nullptr, h->d_scratch[stage], st, stage);
+    };
+    return host_pipe_run(h->pipe, h->dtype, h->N, h->K, chunk, llr_host, llr_dtype, F, out_host, out_format, nullptr, stream,
+                         launch, fail);
 #endif
+}
+
+extern "C" int pcl_polar_decode_host(pcl_polar_t* h, const void* llr_host, int64_t F, uint8_t* bits_host, void* stream)
+{
+    if (!h) return fail(PCL_EINVAL, "bad handle or F");
+    return pcl_polar_decode_host_ex(h, llr_host, h->dtype, F, bits_host, PCL_OUT_BYTES, stream);
 }
 
 // ================================================================ LDPC =========
@@ -562,12 +548,8 @@ struct pcl_ldpc {
     int banked_residual = 0;
     unsigned long long* d_next[PCL_NSTAGE] = {};
     int wpb, grid_max, smem_bytes, last_grid = 0;
-    void* d_llr[PCL_NSTAGE] = {};
-    uint8_t* d_bits[PCL_NSTAGE] = {};
-    int32_t* d_iters[PCL_NSTAGE] = {};
-    int64_t chunk = 0;
 #ifndef PCL_EMU
-    cudaStream_t st[PCL_NSTAGE] = {};
+    HostPipe pipe;              // host-buffer pipeline (pcl_host_pipe.cuh)
 #endif
 };
 
@@ -807,12 +789,10 @@ extern "C" void pcl_ldpc_destroy(pcl_ldpc_t* h)
     if (!h) return;
     cudaFree(h->d_cptr); cudaFree(h->d_col); cudaFree(h->d_vptr); cudaFree(h->d_vperm); cudaFree(h->d_vpack);
     cudaFree(h->d_bpack); cudaFree(h->d_varof); cudaFree(h->d_posof); cudaFree(h->d_cpos);
-    for (int s = 0; s < PCL_NSTAGE; s++) {
-        cudaFree(h->d_next[s]); cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
+    for (int s = 0; s < PCL_NSTAGE; s++) cudaFree(h->d_next[s]);
 #ifndef PCL_EMU
-        if (h->st[s]) cudaStreamDestroy(h->st[s]);
+    h->pipe.destroy();
 #endif
-    }
     delete h;
 }
 
@@ -872,51 +852,37 @@ extern "C" int pcl_ldpc_decode_batch(pcl_ldpc_t* h, const void* llr_dev, int64_t
     return ldpc_decode_impl<float>(h, llr_dev, F, bits_dev, iters_dev, total_dev, h->d_next[0], stream);
 }
 
-extern "C" int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
-                                    int32_t* iters_host, void* stream)
+extern "C" int pcl_ldpc_decode_host_ex(pcl_ldpc_t* h, const void* llr_host, int llr_dtype, int64_t F, void* out_host,
+                                       int out_format, int32_t* iters_host, void* stream)
 {
     if (!h || F < 0) return fail(PCL_EINVAL, "bad handle or F");
     if (F == 0) return PCL_OK;
-    if (!llr_host || !bits_host) return fail(PCL_EINVAL, "null buffer");
+    if (!llr_host || !out_host) return fail(PCL_EINVAL, "null buffer");
 #ifdef PCL_EMU
-    (void)stream; (void)iters_host;
+    (void)stream; (void)iters_host; (void)llr_dtype; (void)out_format;
     return fail(PCL_ECUDA, "no CUDA device");
 #else
-    const size_t rsz = real_size(h->dtype);
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(F, env_int("PCL_HOST_CHUNK", 8192)));
-    if (h->chunk < chunk) {
-        for (int s = 0; s < PCL_NSTAGE; s++) {
-            cudaFree(h->d_llr[s]); cudaFree(h->d_bits[s]); cudaFree(h->d_iters[s]);
-            h->d_llr[s] = nullptr; h->d_bits[s] = nullptr; h->d_iters[s] = nullptr;
-            CUDA_TRY(cudaMalloc(&h->d_llr[s], (size_t)chunk * h->n * rsz));
-            CUDA_TRY(cudaMalloc((void**)&h->d_bits[s], (size_t)chunk * h->n));
-            CUDA_TRY(cudaMalloc((void**)&h->d_iters[s], (size_t)chunk * 4));
-        }
-        h->chunk = chunk;
-    }
-    for (int s = 0; s < PCL_NSTAGE; s++) {
-        if (!h->st[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->st[s], cudaStreamNonBlocking));
+    for (int s = 0; s < PCL_NSTAGE; s++)
         if (!h->d_next[s]) CUDA_TRY(cudaMalloc((void**)&h->d_next[s], 8));
-    }
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    int stage = 0;
-    for (int64_t f0 = 0; f0 < F; f0 += chunk, stage = (stage + 1) % PCL_NSTAGE) {
-        const int64_t fc = std::min<int64_t>(chunk, F - f0);
-        cudaStream_t st = h->st[stage];
-        CUDA_TRY(cudaMemcpyAsync(h->d_llr[stage], (const char*)llr_host + (size_t)f0 * h->n * rsz,
-                                 (size_t)fc * h->n * rsz, cudaMemcpyHostToDevice, st));
-        int rc = (h->dtype == PCL_F64)
-            ? ldpc_decode_impl<double>(h, h->d_llr[stage], fc, h->d_bits[stage], h->d_iters[stage], nullptr, h->d_next[stage], st)
-            : ldpc_decode_impl<float>(h, h->d_llr[stage], fc, h->d_bits[stage], h->d_iters[stage], nullptr, h->d_next[stage], st);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(bits_host + (size_t)f0 * h->n, h->d_bits[stage], (size_t)fc * h->n,
-                                 cudaMemcpyDeviceToHost, st));
-        if (iters_host)
-            CUDA_TRY(cudaMemcpyAsync(iters_host + f0, h->d_iters[stage], (size_t)fc * 4, cudaMemcpyDeviceToHost, st));
-    }
-    for (int s = 0; s < PCL_NSTAGE; s++) CUDA_TRY(cudaStreamSynchronize(h->st[s]));
-    return PCL_OK;
+    const int64_t resident = (int64_t)h->grid_max * (h->lay.coop ? 1 : h->wpb);
+    int64_t chunk = std::max<int64_t>(4 * resident, ((int64_t)32 << 20) / ((int64_t)h->n * 4));
+    chunk = (chunk + 255) / 256 * 256;
+    chunk = env_int("PCL_HOST_CHUNK", (int)std::min<int64_t>(chunk, 1 << 20));
+    PipeLaunch launch = [h](int stage, cudaStream_t st, const void* d_llr, int64_t fc, uint8_t* d_bits, int32_t* d_iters) -> int {
+        return (h->dtype == PCL_F64)
+            ? ldpc_decode_impl<double>(h, d_llr, fc, d_bits, d_iters, nullptr, h->d_next[stage], st)
+            : ldpc_decode_impl<float>(h, d_llr, fc, d_bits, d_iters, nullptr, h->d_next[stage], st);
+    };
+    return host_pipe_run(h->pipe, h->dtype, h->n, h->n, chunk, llr_host, llr_dtype, F, out_host, out_format, iters_host, stream,
+                         launch, fail);
 #endif
+}
+
+extern "C" int pcl_ldpc_decode_host(pcl_ldpc_t* h, const void* llr_host, int64_t F, uint8_t* bits_host,
+                                    int32_t* iters_host, void* stream)
+{
+    if (!h) return fail(PCL_EINVAL, "bad handle or F");
+    return pcl_ldpc_decode_host_ex(h, llr_host, h->dtype, F, bits_host, PCL_OUT_BYTES, iters_host, stream);
 }
 
 // ============================================================ frame generator ===

@@ -100,6 +100,8 @@ class _LdpcBase:
     def decode_batch(self, llr, return_iterations: bool = False, return_total_llr: bool = False):
         """llr[F, n] -> bits[F, n] (+ iterations[F], + total LLRs of the last iteration)."""
         on_device = isinstance(llr, self._torch.Tensor) and llr.is_cuda
+        if not return_total_llr and not isinstance(llr, self._torch.Tensor):
+            return self._decode_numpy(llr, return_iterations)
         bits, iters, total = self._run(self._to_device(llr), return_total_llr)
         out = [bits if on_device else bits.cpu().numpy().astype(np.int64)]
         if return_iterations:
@@ -108,24 +110,55 @@ class _LdpcBase:
             out.append(total if on_device else total.double().cpu().numpy())
         return out[0] if len(out) == 1 else tuple(out)
 
-    def decode_batch_host(self, llr_host, bits_host=None, iters_host=None):
-        """C-ABI host-buffer path (chunked, overlapped H2D / decode / D2H)."""
+    def _decode_numpy(self, llr, return_iterations: bool):
+        """The reference call shape: host float array [F, n] in, np.int64 [F, n] out (+ iterations),
+        through the library's chunked host pipeline (pcl_ldpc_decode_host_ex)."""
+        if self._deferred is not None:
+            raise self._deferred
+        a, code = _native.host_llr(llr, self._code)
+        assert a.ndim == 2 and a.shape[1] == self.n, f"expected LLR shape (F, {self.n}), got {a.shape}"
+        F = a.shape[0]
+        out = np.empty((F, self.n), dtype=np.int64)
+        iters = np.empty(F, dtype=np.int32) if return_iterations else None
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.check(_native.lib().pcl_ldpc_decode_host_ex(
+                self._h, ctypes.c_void_p(a.ctypes.data), code, F, ctypes.c_void_p(out.ctypes.data), _native.PCL_OUT_INT64,
+                ctypes.c_void_p(iters.ctypes.data) if iters is not None else None, ctypes.c_void_p(stream)))
+        return (out, iters.astype(np.int64)) if return_iterations else out
+
+    def decode_batch_host(self, llr_host, bits_host=None, iters_host=None, packed: bool = False):
+        """C-ABI host-buffer path (chunked, overlapped H2D / decode / D2H).  llr_host: CPU tensor [F, n]
+        in the compute dtype or float16 (opt-in transport format for an fp32 decoder); result uint8
+        [F, n], or bit-packed int32 [F, ceil(n / 32)] with packed=True."""
         if self._deferred is not None:
             raise self._deferred
         torch = self._torch
         if not isinstance(llr_host, torch.Tensor):
             llr_host = torch.from_numpy(np.ascontiguousarray(llr_host))
-        assert llr_host.dim() == 2 and llr_host.shape[1] == self.n and llr_host.dtype == self._tdtype
+        f16 = llr_host.dtype == torch.float16 and self._code == _native.PCL_F32
+        assert llr_host.dim() == 2 and llr_host.shape[1] == self.n and (llr_host.dtype == self._tdtype or f16)
         assert llr_host.device.type == "cpu" and llr_host.is_contiguous()
         F = llr_host.shape[0]
+        shape, dt, fmt = ((F, (self.n + 31) // 32), torch.int32, _native.PCL_OUT_PACKED) if packed else \
+                         ((F, self.n), torch.uint8, _native.PCL_OUT_BYTES)
         if bits_host is None:
-            bits_host = torch.empty((F, self.n), dtype=torch.uint8, pin_memory=True)
+            bits_host = torch.empty(shape, dtype=dt, pin_memory=True)
+        # the library writes through these pointers: refuse anything that is not exactly the expected buffer
+        assert isinstance(bits_host, torch.Tensor) and bits_host.device.type == "cpu" and bits_host.dtype == dt \
+            and bits_host.is_contiguous() and tuple(bits_host.shape) == shape, \
+            f"bits_host must be a contiguous CPU {dt} tensor of shape {shape}"
+        if iters_host is not None:
+            assert isinstance(iters_host, torch.Tensor) and iters_host.device.type == "cpu" and \
+                iters_host.dtype == torch.int32 and iters_host.is_contiguous() and iters_host.numel() == F, \
+                f"iters_host must be a contiguous CPU int32 tensor with {F} elements"
         ip = ctypes.c_void_p(iters_host.data_ptr()) if iters_host is not None else None
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _native.check(_native.lib().pcl_ldpc_decode_host(
-                self._h, ctypes.c_void_p(llr_host.data_ptr()), F, ctypes.c_void_p(bits_host.data_ptr()), ip,
-                ctypes.c_void_p(stream)))
+            _native.check(_native.lib().pcl_ldpc_decode_host_ex(
+                self._h, ctypes.c_void_p(llr_host.data_ptr()), _native.PCL_F16 if f16 else self._code, F,
+                ctypes.c_void_p(bits_host.data_ptr()), fmt, ip, ctypes.c_void_p(stream)))
         return bits_host
 
     def launch_info(self) -> dict:

@@ -120,18 +120,56 @@ class _PolarBase:
                 "frames_per_warp": (32 // self._LP) if fa.value else 1,
                 "compiled_code_length": fa.value >= 2, "tensor_memory": fa.value == 3}
 
-    def decode_batch_host(self, llr_host, bits_host=None):
-        """C-ABI host-buffer path: llr_host is a CPU tensor/array [F, N] in the compute
-        dtype (pinned memory makes the copies asynchronous); returns uint8 [F, K] on host.
-        H2D, decode and D2H are chunked and overlapped inside the library."""
+    def _decode_numpy(self, llr) -> np.ndarray:
+        """The reference call shape: host float array [F, N] in, np.int64 [F, K] out, through the
+        library's chunked host pipeline (pcl_polar_decode_host_ex: conversion threads, pinned
+        staging, H2D, decode, packed D2H and unpacking overlap)."""
+        a, code = _native.host_llr(llr, self._code)
+        assert a.ndim == 2 and a.shape[1] == self.N, f"expected LLR shape (F, {self.N}), got {a.shape}"
+        out = np.empty((a.shape[0], self._K_out), dtype=np.int64)
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.check(_native.lib().pcl_polar_decode_host_ex(
+                self._h, ctypes.c_void_p(a.ctypes.data), code, a.shape[0], ctypes.c_void_p(out.ctypes.data),
+                _native.PCL_OUT_INT64, ctypes.c_void_p(stream)))
+        return out
+
+    def decode_batch_host(self, llr_host, bits_host=None, packed: bool = False):
+        """C-ABI host-buffer path: llr_host is a CPU tensor/array [F, N] in the compute dtype, or
+        float16 as an opt-in TRANSPORT format for an fp32 decoder (half the PCIe bytes; the decoder then
+        sees the fp16-rounded LLRs).  Pinned memory makes the copies asynchronous.  Returns uint8 [F, K]
+        on host, or with packed=True the bit-packed rows int32 [F, ceil(K / 32)] (bit k of a row at word
+        k // 32, bit k % 32; packed on the device, 1/8 of the D2H bytes).  H2D, decode and D2H are
+        chunked and overlapped inside the library."""
         torch = self._torch
         if not isinstance(llr_host, torch.Tensor):
             llr_host = torch.from_numpy(np.ascontiguousarray(llr_host))
-        assert llr_host.dim() == 2 and llr_host.shape[1] == self.N and llr_host.dtype == self._tdtype
+        f16 = llr_host.dtype == torch.float16 and self._code == _native.PCL_F32
+        assert llr_host.dim() == 2 and llr_host.shape[1] == self.N and (llr_host.dtype == self._tdtype or f16)
         assert llr_host.device.type == "cpu" and llr_host.is_contiguous()
         F = llr_host.shape[0]
+        if packed or f16:
+            words = (self._K_out + 31) // 32
+            shape, dt, fmt = ((F, words), torch.int32, _native.PCL_OUT_PACKED) if packed else \
+                             ((F, self._K_out), torch.uint8, _native.PCL_OUT_BYTES)
+            if bits_host is None:
+                bits_host = torch.empty(shape, dtype=dt, pin_memory=True)
+            assert isinstance(bits_host, torch.Tensor) and bits_host.device.type == "cpu" and bits_host.dtype == dt \
+                and bits_host.is_contiguous() and tuple(bits_host.shape) == shape, \
+                f"bits_host must be a contiguous CPU {dt} tensor of shape {shape}"
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                _native.check(_native.lib().pcl_polar_decode_host_ex(
+                    self._h, ctypes.c_void_p(llr_host.data_ptr()), _native.PCL_F16 if f16 else self._code, F,
+                    ctypes.c_void_p(bits_host.data_ptr()), fmt, ctypes.c_void_p(stream)))
+            return bits_host
         if bits_host is None:
             bits_host = torch.empty((F, self._K_out), dtype=torch.uint8, pin_memory=True)
+        # the library writes F * K bytes through this pointer: refuse anything that is not exactly that
+        assert isinstance(bits_host, torch.Tensor) and bits_host.device.type == "cpu" and bits_host.dtype == torch.uint8 \
+            and bits_host.is_contiguous() and tuple(bits_host.shape) == (F, self._K_out), \
+            f"bits_host must be a contiguous CPU uint8 tensor of shape ({F}, {self._K_out})"
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             _native.check(_native.lib().pcl_polar_decode_host(
@@ -145,22 +183,41 @@ class SCDecoder(_PolarBase):
 
     def __init__(self, N: int, K: int, frozen_bits: Optional[np.ndarray] = None, dtype=None, device=None):
         self._setup(N, K, 1, frozen_bits, False, "CRC-8", dtype, device)
-        # the reference's LLR / bit matrices (decoder.py:35-36); decode() fills the
-        # channel column and the leaf column, the only ones callers read.
-        self.L = np.full((N, self.n + 1), np.nan, dtype=np.float64)
-        self.B = np.full((N, self.n + 1), np.nan, dtype=np.float64)
+        # the reference's LLR / bit matrices (decoder.py:35-36).  Callers read the channel column and
+        # the leaf column (debug_scripts/compare_step_by_step.py:40-47); they are filled LAZILY, on the
+        # first read of .L / .B after a decode(), so decode() itself is one kernel launch.
+        self._L = np.full((N, self.n + 1), np.nan, dtype=np.float64)
+        self._B = np.full((N, self.n + 1), np.nan, dtype=np.float64)
+        self._pending = None                    # (llr_input, decoded bits) of the last decode()
+
+    def _materialise(self):
+        if self._pending is None:
+            return
+        llr_input, out = self._pending
+        self._pending = None
+        _, _, leaf, par = self._run(self._to_device(llr_input[None, :]), False, True)
+        self._L[:, 0] = llr_input
+        self._L[:, self.n] = self._leaf_of_best(None, leaf, par)[0].double().cpu().numpy()
+        u = np.zeros(self.N)
+        u[self.info_bits] = out
+        self._B[:, self.n] = u
+
+    @property
+    def L(self) -> np.ndarray:
+        self._materialise()
+        return self._L
+
+    @property
+    def B(self) -> np.ndarray:
+        self._materialise()
+        return self._B
 
     def decode(self, llr_input: np.ndarray) -> np.ndarray:
         llr_input = np.asarray(llr_input, dtype=np.float64)
         assert llr_input.shape == (self.N,), f"expected LLR shape ({self.N},), got {llr_input.shape}"
-        bits, _, leaf, par = self._run(self._to_device(llr_input[None, :]), False, True)
-        leaf_ref = self._leaf_of_best(None, leaf, par)[0].double().cpu().numpy()
+        bits, _, _, _ = self._run(self._to_device(llr_input[None, :]), False, False)
         out = bits[0].cpu().numpy().astype(np.int64)
-        self.L[:, 0] = llr_input
-        self.L[:, self.n] = leaf_ref
-        u = np.zeros(self.N)
-        u[self.info_bits] = out
-        self.B[:, self.n] = u
+        self._pending = (llr_input.copy(), out)
         return out
 
     def decode_batch(self, llr, return_leaf_llr: bool = False):
@@ -169,6 +226,8 @@ class SCDecoder(_PolarBase):
         numpy in -> np.int64 out (what F decode() calls would return); CUDA tensor in ->
         uint8 CUDA tensor out, no host sync.  return_leaf_llr adds L[:, n] per frame."""
         on_device = isinstance(llr, self._torch.Tensor) and llr.is_cuda
+        if not return_leaf_llr and not isinstance(llr, self._torch.Tensor):
+            return self._decode_numpy(llr)
         bits, _, leaf, par = self._run(self._to_device(llr), False, return_leaf_llr)
         res = bits if on_device else bits.cpu().numpy().astype(np.int64)
         if return_leaf_llr:
@@ -205,6 +264,8 @@ class SCLDecoder(_PolarBase):
         """llr[F, N] -> info bits [F, K] (+ path_metrics[F, L], + L_paths[best, :, n])."""
         on_device = isinstance(llr, self._torch.Tensor) and llr.is_cuda
         want_pm = return_path_metrics or return_leaf_llr
+        if not want_pm and not isinstance(llr, self._torch.Tensor):
+            return self._decode_numpy(llr)
         bits, pm, leaf, par = self._run(self._to_device(llr), want_pm, return_leaf_llr)
         out = [bits if on_device else bits.cpu().numpy().astype(np.int64)]
         if return_path_metrics:

@@ -142,6 +142,41 @@ def test_emu_polar_global_levels_and_crc():
                                                env={"PCL_POLAR_GENERIC": generic}), ref_crc)
 
 
+def test_emu_polar_tensor_memory_variant():
+    """The one-block-per-SM variant of the fast kernel (tensor-memory / shared-memory mid levels, level 3
+    fused from the channel through the cp.async ring, ticket-scheduled warp groups) on the SIMT emulator,
+    both lane orders: bits of the oracle for SCL-8 N = 1024 with more chunks than warp groups."""
+    N, K, L = 1024, 512, 8
+    fz = P.bhattacharyya_frozen_set(N, K, 2.0)
+    enc = P.PolarEncoder(N, K, fz)
+    rng = np.random.default_rng(3)
+    np.random.seed(5)
+    llr = P.AWGNChannel(-1.0).transmit_batch(enc.encode_batch(rng.integers(0, 2, size=(37, K))))
+    ref = oracle.polar_scl(N, L, fz, llr)
+    for reverse in (False, True):
+        got = emu.polar_decode(N, K, L, fz, llr, "f32", reverse=reverse)
+        assert emu.polar_decode.last_fast == 3
+        assert np.array_equal(got, ref)
+    got = emu.polar_decode(N, K, L, fz, llr[:9], "f32", env={"PCL_POLAR_TM": 0})
+    assert emu.polar_decode.last_fast == 2 and np.array_equal(got, ref[:9])
+
+
+def test_emu_polar_large_code_falls_back_instead_of_failing():
+    """N = 8192 with list size 1 (and with CRC selection) used to be refused: the fast kernel's bit
+    arrays need 32-64 KB per warp whatever the list size.  The handle now retries with fewer warps per
+    block and then with the generic kernel."""
+    N, K = 8192, 4096
+    fz = P.bhattacharyya_frozen_set(N, K, 2.0)
+    rng = np.random.default_rng(4)
+    np.random.seed(4)
+    llr = P.AWGNChannel(2.0).transmit_batch(P.PolarEncoder(N, K, fz).encode_batch(rng.integers(0, 2, size=(2, K))))
+    assert np.array_equal(emu.polar_decode(N, K, 1, fz, llr, "f32"), oracle.polar_sc(N, fz, llr))
+    enc = P.PolarEncoder(N, K, fz, use_crc=True)
+    llr = P.AWGNChannel(2.0).transmit_batch(enc.encode_batch(rng.integers(0, 2, size=(1, enc.K_data))))
+    ref = oracle.polar_scl(N, 2, fz, llr, use_crc=True)
+    assert np.array_equal(emu.polar_decode(N, K, 2, fz, llr, "f32", crc=(0x1D, 8)), ref)
+
+
 def test_emu_ldpc_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "ldpc.npz"))
     for name in g["names"]:
