@@ -26,8 +26,11 @@
 // the check pass moves two messages per 8-byte access (conflict free), an edge's bank becomes
 // 2 (lane % 16) + (k & 1), and the host search also decides which half of a check's edges sit
 // at odd k.
+// One warp per frame (COOP = 0): the library launches ONE block per SM holding every warp the SM's
+// shared memory has room for (up to 32), so the residency cannot depend on which shared-memory /
+// L1 split the SM happens to be in when the grid arrives.
 template <int MODE, int DC, int COOP, int PAIRED>
-__global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
+__global__ void __launch_bounds__(COOP ? 256 : 1024) ldpc_banked_kernel(LdpcParams<float> P)
 {
     const LdpcLayout& Y = P.lay;
     const int n = Y.n, nR = Y.nR, NP = Y.NP, NS = Y.NS;
@@ -50,11 +53,11 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
     for (;;) {
         unsigned long long fq = 0;
         if (coop) {
-            if (tid == 0) ctl[0] = atomicAdd(P.next, 1ull);
+            if (tid == 0) ctl[0] = atomicAdd(P.next, 1ull) - P.ticket_base;
             __syncthreads();
             fq = ctl[0];
         } else {
-            if (lane == 0) fq = atomicAdd(P.next, 1ull);
+            if (lane == 0) fq = atomicAdd(P.next, 1ull) - P.ticket_base;
             fq = pcl_shfl_u64(fq, 0);
         }
         if ((int64_t)fq >= P.F) break;
@@ -76,7 +79,35 @@ __global__ void __launch_bounds__(256) ldpc_banked_kernel(LdpcParams<float> P)
         int iters = Y.max_iter;
         for (int it = 0; it < Y.max_iter; it++) {
             // 1. check nodes: round R, lane = the check's bank (an empty seat computes on zeros)
-            for (int R = w0; R < nR; R += wstep) {
+            int R = w0;
+#if !defined(PCL_LDPC_NO_PAIR2)
+            if (MODE == 0 && PAIRED) {
+                // BP: two rounds per step, the two checks of a lane side by side on the fp32x2 pipe
+                for (; R + wstep < nR; R += 2 * wstep) {
+                    float* ba = msg + 32 * DC * R + 2 * lane;
+                    float* bb = ba + 32 * DC * wstep;
+                    uint32_t xa[DC], xb2[DC];
+                    float oa[DC], ob[DC];
+#pragma unroll
+                    for (int k = 0; k < DC; k += 2) {
+                        const float2 va = *reinterpret_cast<const float2*>(ba + 32 * k);
+                        const float2 vb = *reinterpret_cast<const float2*>(bb + 32 * k);
+                        xa[k] = __float_as_uint(va.x); xa[k + 1] = __float_as_uint(va.y);
+                        xb2[k] = __float_as_uint(vb.x); xb2[k + 1] = __float_as_uint(vb.y);
+                    }
+                    cn_bp_core2<DC>(xa, xb2, oa, ob);
+#pragma unroll
+                    for (int k = 0; k < DC; k += 2) {
+                        float2 va, vb;
+                        va.x = oa[k]; va.y = oa[k + 1];
+                        vb.x = ob[k]; vb.y = ob[k + 1];
+                        *reinterpret_cast<float2*>(ba + 32 * k) = va;
+                        *reinterpret_cast<float2*>(bb + 32 * k) = vb;
+                    }
+                }
+            }
+#endif
+            for (; R < nR; R += wstep) {
                 float* base = msg + 32 * DC * R + (PAIRED ? 2 * lane : lane);
                 float x[DC], out[DC];
                 if (PAIRED) {

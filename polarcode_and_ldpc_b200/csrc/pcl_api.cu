@@ -463,6 +463,7 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
     int grid = (int)std::min<int64_t>(need, h->grid_max);
     P.next = nullptr;
     P.ticket_base = 0;
+    unsigned long long advance = 0;
     if (h->TM) {
         // groups of 4 warps pull chunks of 4 fpw frames; a small batch spreads its chunks over the SMs
         const int64_t chunks = (F + 4 * h->fpw - 1) / (4 * h->fpw);
@@ -470,12 +471,13 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
         P.next = h->d_next[stage];
         P.ticket_base = h->tickets[stage];
         // every group fetches until it draws a ticket past the end: chunks + one per group
-        h->tickets[stage] += (unsigned long long)chunks + (unsigned long long)grid * (h->wpb / 4);
+        advance = (unsigned long long)chunks + (unsigned long long)grid * (h->wpb / 4);
     }
     h->last_grid = grid;
     int rc = polar_launch<real>(h, P, grid, stream);
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
+    h->tickets[stage] += advance;              // only a launch that went out draws tickets
     return PCL_OK;
 }
 
@@ -547,6 +549,7 @@ struct pcl_ldpc {
     uint16_t* d_cpos = nullptr;
     int banked_residual = 0;
     unsigned long long* d_next[PCL_NSTAGE] = {};
+    unsigned long long tickets[PCL_NSTAGE] = {};   // value of each counter (no memset between launches)
     int wpb, grid_max, smem_bytes, last_grid = 0;
 #ifndef PCL_EMU
     HostPipe pipe;              // host-buffer pipeline (pcl_host_pipe.cuh)
@@ -736,6 +739,13 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
         Y.coop = coop ? 1 : 0;
         if (Y.coop) h->wpb = 4;
     }
+    if (!Y.coop && Y.banked && env_int("PCL_LDPC_FAT", 1) != 0 && env_int("PCL_LDPC_WPB", 0) < 1) {
+        // warp-per-frame banked kernel: one fat block per SM when a single block can hold everything the
+        // SM's shared memory has room for (deterministic residency, see ldpc_banked.cuh)
+        const int fat = std::min(32, (std::min(di.smem_per_sm - 1024, di.smem_per_block)) / Y.warp_bytes);
+        const int now = (di.smem_per_sm / (Y.warp_bytes * h->wpb + 1024)) * h->wpb;
+        if (fat >= now && fat >= 1) h->wpb = fat;
+    }
     h->smem_bytes = Y.coop ? Y.warp_bytes : Y.warp_bytes * h->wpb;
     if (h->smem_bytes > di.smem_per_block) {
         const int need = Y.warp_bytes;           // Y lives inside *h
@@ -755,7 +765,7 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
               cudaMalloc((void**)&h->d_col, std::max(E, 1) * 2) == cudaSuccess &&
               cudaMalloc((void**)&h->d_vptr, (n + 1) * 4) == cudaSuccess &&
               cudaMalloc((void**)&h->d_vperm, std::max(E, 1) * 2) == cudaSuccess &&
-              cudaMalloc((void**)&h->d_next[0], 8) == cudaSuccess;
+              cudaMalloc((void**)&h->d_next[0], 8) == cudaSuccess && cudaMemset(h->d_next[0], 0, 8) == cudaSuccess;
     ok = ok && cudaMemcpy(h->d_cptr, cptr.data(), (m + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(h->d_vptr, vptr.data(), (n + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok && E)
@@ -818,8 +828,9 @@ extern "C" int pcl_ldpc_launch_info(const pcl_ldpc_t* h, int* grid, int* block, 
 
 template <typename real>
 static int ldpc_decode_impl(pcl_ldpc* h, const void* llr_dev, int64_t F, uint8_t* bits_dev, int32_t* iters_dev,
-                            void* total_dev, unsigned long long* next, void* stream)
+                            void* total_dev, int stage, void* stream)
 {
+    unsigned long long* next = h->d_next[stage];
     LdpcParams<real> P;
     P.lay = h->lay;
     P.llr = (const real*)llr_dev;
@@ -831,13 +842,18 @@ static int ldpc_decode_impl(pcl_ldpc* h, const void* llr_dev, int64_t F, uint8_t
     P.next = next;
     P.F = F;
     P.norm = (real)h->norm;
-    CUDA_TRY(cudaMemsetAsync(next, 0, 8, (cudaStream_t)stream));
     int64_t need = h->lay.coop ? F : (F + h->wpb - 1) / h->wpb;
     int grid = (int)std::min<int64_t>(need, h->grid_max);
     h->last_grid = grid;
+    // every fetching unit (a warp, or a block in the block-per-frame mode) draws tickets until one is past
+    // the end: F + units draws per launch, so the counter needs no reset (a memset between two decode
+    // kernels is one more foreign launch that can leave the SMs in another shared-memory split)
+    P.ticket_base = h->tickets[stage];
+    const unsigned long long advance = (unsigned long long)F + (unsigned long long)grid * (h->lay.coop ? 1 : h->wpb);
     int rc = ldpc_launch<real>(h, P, grid, stream);
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
+    h->tickets[stage] += advance;              // only a launch that went out draws tickets
     return PCL_OK;
 }
 
@@ -848,8 +864,8 @@ extern "C" int pcl_ldpc_decode_batch(pcl_ldpc_t* h, const void* llr_dev, int64_t
     if (F == 0) return PCL_OK;
     if (!llr_dev || !bits_dev) return fail(PCL_EINVAL, "null buffer");
     if (h->dtype == PCL_F64)
-        return ldpc_decode_impl<double>(h, llr_dev, F, bits_dev, iters_dev, total_dev, h->d_next[0], stream);
-    return ldpc_decode_impl<float>(h, llr_dev, F, bits_dev, iters_dev, total_dev, h->d_next[0], stream);
+        return ldpc_decode_impl<double>(h, llr_dev, F, bits_dev, iters_dev, total_dev, 0, stream);
+    return ldpc_decode_impl<float>(h, llr_dev, F, bits_dev, iters_dev, total_dev, 0, stream);
 }
 
 extern "C" int pcl_ldpc_decode_host_ex(pcl_ldpc_t* h, const void* llr_host, int llr_dtype, int64_t F, void* out_host,
@@ -863,15 +879,19 @@ extern "C" int pcl_ldpc_decode_host_ex(pcl_ldpc_t* h, const void* llr_host, int 
     return fail(PCL_ECUDA, "no CUDA device");
 #else
     for (int s = 0; s < PCL_NSTAGE; s++)
-        if (!h->d_next[s]) CUDA_TRY(cudaMalloc((void**)&h->d_next[s], 8));
+        if (!h->d_next[s]) {
+            CUDA_TRY(cudaMalloc((void**)&h->d_next[s], 8));
+            CUDA_TRY(cudaMemset(h->d_next[s], 0, 8));
+            h->tickets[s] = 0;
+        }
     const int64_t resident = (int64_t)h->grid_max * (h->lay.coop ? 1 : h->wpb);
     int64_t chunk = std::max<int64_t>(4 * resident, ((int64_t)32 << 20) / ((int64_t)h->n * 4));
     chunk = (chunk + 255) / 256 * 256;
     chunk = env_int("PCL_HOST_CHUNK", (int)std::min<int64_t>(chunk, 1 << 20));
     PipeLaunch launch = [h](int stage, cudaStream_t st, const void* d_llr, int64_t fc, uint8_t* d_bits, int32_t* d_iters) -> int {
         return (h->dtype == PCL_F64)
-            ? ldpc_decode_impl<double>(h, d_llr, fc, d_bits, d_iters, nullptr, h->d_next[stage], st)
-            : ldpc_decode_impl<float>(h, d_llr, fc, d_bits, d_iters, nullptr, h->d_next[stage], st);
+            ? ldpc_decode_impl<double>(h, d_llr, fc, d_bits, d_iters, nullptr, stage, st)
+            : ldpc_decode_impl<float>(h, d_llr, fc, d_bits, d_iters, nullptr, stage, st);
     };
     return host_pipe_run(h->pipe, h->dtype, h->n, h->n, chunk, llr_host, llr_dtype, F, out_host, out_format, iters_host, stream,
                          launch, fail);
