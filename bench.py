@@ -320,11 +320,19 @@ def run_gpu_workload(name, steps, warmup, env, snr=None, frames=None, with_e2e=F
         counters.add(0, bits, ref, None)
     counters.allreduce()                       # warms the exact collective of the timed region
     counters.t.zero_()
+    start_line = torch.zeros(1, device=device)
+    if world > 1:
+        dist.all_reduce(start_line)
     barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
     if rank == 0:
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 2)]
+    if world > 1:
+        # GPU-side start line: the host threads leave barrier() milliseconds apart; this collective is
+        # queued ahead of the first event, so every rank's timed region opens when the LAST rank's
+        # stream arrives and the closing allreduce no longer measures the hosts' skew
+        dist.all_reduce(start_line)
     ev[0].record()
     for s in range(steps):
         bits = dec.decode_batch(llr)
