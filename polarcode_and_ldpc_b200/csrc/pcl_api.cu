@@ -8,6 +8,7 @@
 #include "pcl_common.cuh"
 #include "polar_scl.cuh"
 #include "polar_scl_fast.cuh"
+#include "polar_sc.cuh"
 #include "framegen.cuh"
 #include "ldpc_banked.cuh"
 #include "ldpc_layout.h"
@@ -127,6 +128,9 @@ struct pcl_polar {
     int fpw = 1;                // fast kernel: frames per warp
     int NL = 0, GL = 0;         // fast kernel: compiled-in log2 N and G (0: run-time values)
     int TM = 0;                 // fast kernel, TM variant: one block per SM, mid levels in tensor / shared memory
+    int sc256 = 0;              // list size 1, N = 256, fp32: the register-resident SC kernel (polar_sc.cuh)
+    uint32_t* d_uwords[PCL_NSTAGE] = {};   // its decision words [F][8], per host-pipeline stage
+    int64_t uwords_cap[PCL_NSTAGE] = {};
     unsigned long long* d_next[PCL_NSTAGE] = {};   // TM variant: ticket counters (one per host-pipeline stage)
     unsigned long long tickets[PCL_NSTAGE] = {};   // their current values (never reset: no memset between launches)
 #ifndef PCL_EMU
@@ -147,7 +151,7 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
         Y.N = N; Y.n = ilog2i(N); Y.K = K; Y.L = L; Y.G = Y.n - 7;
         Y.NW = N / 32; Y.nb = Y.n - 5;
         Y.uw_slots = crc ? cols : fpw;
-        Y.hdr_bytes = 128;
+        Y.hdr_bytes = 256;                          // TMEM base + two 8-byte ticket slots per group of warps
         int off = 0;
         Y.off_cm = off;     off += fpw * pcl_fast_frame_bytes(LP);
         Y.off_newpm = off;
@@ -196,7 +200,7 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
 #define PCL_POLAR_FAST_VARIANTS(X) \
     X(1, 0, 0, 0) X(2, 0, 0, 0) X(4, 0, 0, 0) X(8, 0, 0, 0) X(16, 0, 0, 0) X(32, 0, 0, 0) \
     X(8, 7, 1, 0) X(8, 8, 2, 0) X(8, 9, 4, 0) X(8, 10, 5, 0) X(8, 11, 7, 0) X(8, 12, 8, 0) X(32, 10, 5, 0) X(1, 8, 2, 0) \
-    X(8, 10, 3, 1)
+    X(8, 10, 3, 1) X(32, 10, 3, 1)
 #endif
 // (SCL-8 gains 1.2-1.9 x from a compiled code length at every N = 128 .. 4096.  SC, LP = 1, does
 // not in general -- N = 1024: 29 Gbps compiled vs 40 at run time; with no prune its time is all
@@ -316,7 +320,7 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     // with fewer warps per block (4, 2, 1) and then falls back to the next kernel in the list.
     const bool can_fast = n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 && env_int("PCL_POLAR_GENERIC", 0) == 0;
     const bool can_tm = can_fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && env_int("PCL_POLAR_TM", 1) != 0 &&
-                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1);
+                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 0) != 0);
     int bps = 1;
     bool placed = false;
     for (int attempt = can_tm ? 0 : (can_fast ? 1 : 2); attempt < 3 && !placed; attempt++) {
@@ -335,8 +339,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
 #else
             int w = env_int("PCL_POLAR_WPB", PCL_POLAR_TM_THREADS / 32);
 #endif
-            w = std::max(4, std::min(w, PCL_POLAR_TM_THREADS / 32)) & ~3;
-            while (w > 4 && h->lay.hdr_bytes + h->lay.warp_bytes * w > di.smem_per_block) w -= 4;
+            w = std::max(PCL_POLAR_TM_GROUP, std::min(w, PCL_POLAR_TM_THREADS / 32)) / PCL_POLAR_TM_GROUP * PCL_POLAR_TM_GROUP;
+            while (w > PCL_POLAR_TM_GROUP && h->lay.hdr_bytes + h->lay.warp_bytes * w > di.smem_per_block) w -= PCL_POLAR_TM_GROUP;
             h->wpb = w;
             h->smem_bytes = h->lay.hdr_bytes + h->lay.warp_bytes * w;
             if (h->smem_bytes > di.smem_per_block) continue;
@@ -394,7 +398,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
         pcl_polar_destroy(h);
         return fail(PCL_ECUDA, "cudaMemcpy failed (tables)");
     }
-    if (h->TM) {
+    h->sc256 = (list_size == 1 && N == 256 && dtype == PCL_F32 && crc_len == 0 && env_int("PCL_POLAR_SC256", 1) != 0) ? 1 : 0;
+    if (h->TM || h->sc256) {
         if (cudaMalloc((void**)&h->d_next[0], 8) != cudaSuccess || cudaMemset(h->d_next[0], 0, 8) != cudaSuccess) {
             pcl_polar_destroy(h);
             return fail(PCL_ECUDA, "cudaMalloc failed (ticket counter)");
@@ -418,6 +423,7 @@ extern "C" void pcl_polar_destroy(pcl_polar_t* h)
     for (int s = 0; s < PCL_NSTAGE; s++) {
         cudaFree(h->d_scratch[s]);
         cudaFree(h->d_next[s]);
+        cudaFree(h->d_uwords[s]);
     }
 #ifndef PCL_EMU
     h->pipe.destroy();
@@ -431,7 +437,7 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
                                      int* fast)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
-    if (fast) *fast = h->fast ? (h->TM ? 3 : (h->NL ? 2 : 1)) : 0;
+    if (fast) *fast = h->sc256 ? 4 : (h->fast ? (h->TM ? 3 : (h->NL ? 2 : 1)) : 0);
     if (grid) *grid = h->last_grid;
     if (block) *block = h->wpb * 32;
     if (smem_bytes) *smem_bytes = h->smem_bytes;
@@ -439,10 +445,57 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
     return PCL_OK;
 }
 
+// SC, N = 256, fp32, nothing but the bits asked for: register-resident kernel + bit gather
+static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint8_t* bits_dev, void* stream, int stage)
+{
+    if (h->uwords_cap[stage] < F) {
+        cudaFree(h->d_uwords[stage]);
+        h->d_uwords[stage] = nullptr;
+        h->uwords_cap[stage] = 0;
+        const int64_t cap = std::max<int64_t>(F, 4096);
+        CUDA_TRY(cudaMalloc((void**)&h->d_uwords[stage], (size_t)cap * 8 * 4));
+        h->uwords_cap[stage] = cap;
+    }
+    if (!h->d_next[stage]) {
+        CUDA_TRY(cudaMalloc((void**)&h->d_next[stage], 8));
+        CUDA_TRY(cudaMemset(h->d_next[stage], 0, 8));
+        h->tickets[stage] = 0;
+    }
+    PolarScParams P;
+    P.llr = (const float*)llr_dev;
+    P.uwords = h->d_uwords[stage];
+    P.frozen_words = h->d_frozen_words;
+    P.next = h->d_next[stage];
+    P.ticket_base = h->tickets[stage];
+    P.F = F;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    const int wpb = 8;
+    const int64_t warps_needed = (F + 31) / 32;
+    const int grid = (int)std::min<int64_t>((warps_needed + wpb - 1) / wpb, (int64_t)di.sms * 2);
+    h->last_grid = grid;
+    PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, 0, stream, P);
+    CUDA_TRY(cudaGetLastError());
+    h->tickets[stage] += (unsigned long long)warps_needed + (unsigned long long)grid * wpb;
+#ifdef PCL_EMU
+    struct Ex { const uint32_t* u; const uint16_t* ip; int64_t F; int NW, K; uint8_t* b; } ex{h->d_uwords[stage], h->d_info_pos, F, 8, h->K, bits_dev};
+    auto run = [](Ex e) { polar_sc_extract_kernel(e.u, e.ip, e.F, e.NW, e.K, e.b); };
+    PCL_LAUNCH(run, 2, 256, 0, stream, ex);
+#else
+    const int egrid = (int)std::min<int64_t>((F * h->K + 255) / 256, (int64_t)di.sms * 8);
+    polar_sc_extract_kernel<<<egrid, 256, 0, (cudaStream_t)stream>>>(h->d_uwords[stage], h->d_info_pos, F, 8, h->K, bits_dev);
+    CUDA_TRY(cudaGetLastError());
+#endif
+    return PCL_OK;
+}
+
 template <typename real>
 static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8_t* bits_dev, double* pm_dev,
                              void* leaf_dev, uint8_t* parent_dev, void* scratch, void* stream, int stage = 0)
 {
+    if (h->sc256 && pm_dev == nullptr && leaf_dev == nullptr && sizeof(real) == 4)
+        return polar_sc256_decode(h, llr_dev, F, bits_dev, stream, stage);
     PolarParams<real> P;
     P.lay = h->lay;
     P.llr = (const real*)llr_dev;
@@ -465,13 +518,13 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
     P.ticket_base = 0;
     unsigned long long advance = 0;
     if (h->TM) {
-        // groups of 4 warps pull chunks of 4 fpw frames; a small batch spreads its chunks over the SMs
-        const int64_t chunks = (F + 4 * h->fpw - 1) / (4 * h->fpw);
+        // groups of PCL_POLAR_TM_GROUP warps pull chunks of frames; a small batch spreads its chunks over the SMs
+        const int64_t chunks = (F + PCL_POLAR_TM_GROUP * h->fpw - 1) / (PCL_POLAR_TM_GROUP * h->fpw);
         grid = (int)std::min<int64_t>(chunks, h->grid_max);
         P.next = h->d_next[stage];
         P.ticket_base = h->tickets[stage];
         // every group fetches until it draws a ticket past the end: chunks + one per group
-        advance = (unsigned long long)chunks + (unsigned long long)grid * (h->wpb / 4);
+        advance = (unsigned long long)chunks + (unsigned long long)grid * (h->wpb / PCL_POLAR_TM_GROUP);
     }
     h->last_grid = grid;
     int rc = polar_launch<real>(h, P, grid, stream);

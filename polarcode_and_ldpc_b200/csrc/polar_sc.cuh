@@ -1,0 +1,149 @@
+// polar_sc.cuh -- dedicated successive-cancellation (list size 1) decoder for N = 256, the
+// reference's quick-start configuration (BASELINE configs[0]; SCDecoder.decode,
+// /root/reference/src/polar/decoder.py:38-115).
+//
+// SC needs no path metric, no prune and no path copies, so the list kernel's machinery is dead
+// weight.  Here a LANE decodes a whole frame and the decoder's entire state lives in registers:
+//   * the tree is cut at the 32-leaf level: level 3 (32 LLRs) comes straight from the channel --
+//     element k from the eight consecutive values at 8 br(k), as in pcl_level3_fused -- and the five
+//     levels below it are a fully unrolled recursion (sc_node<32>), every array index a constant;
+//   * partial sums are bit words: one word per 32-leaf node, folded upwards into the left arrays of
+//     levels 3, 2 and 1 (1 + 2 + 4 registers);
+//   * a frozen subtree costs nothing at all: its decisions are zero and, without a path metric,
+//     nobody needs its LLRs (the reference computes them and throws them away) -- the whole visit,
+//     channel loads included, is skipped behind a warp-uniform branch;
+//   * the decisions leave as one 32-bit word per node, u[f][N / 32]; a second, HBM-bound kernel
+//     gathers the K information bits into the byte rows of the C ABI.
+// Arithmetic: f = sign sign min (one FMNMX.XORSIGN), g = b + (1 - 2u) a, decision bit = [x < 0]
+// exactly as decoder.py:58-66, :121-144 -- in fp32; the fp64 validation build keeps the list kernel.
+#pragma once
+#include "pcl_common.cuh"
+
+struct PolarScParams {
+    const float* llr;               // [F][N] channel LLRs, reference index order
+    uint32_t* uwords;               // [F][N / 32] decisions, decode-step order
+    const uint32_t* frozen_words;   // decode-step-order frozen mask (N / 32 words)
+    unsigned long long* next;       // ticket counter: a warp pulls 32 frames per ticket
+    unsigned long long ticket_base;
+    int64_t F;
+};
+
+PCL_DEVICE float sc_g(float a, float b, uint32_t bit_at_31)
+{
+    return b + __uint_as_float(__float_as_uint(a) ^ (bit_at_31 & 0x80000000u));
+}
+
+// One node of SZ leaves whose LLRs a[0 .. SZ) sit in registers.  fz: SZ frozen flags (uniform over the
+// warp), returns the node's partial sums (SZ bits), u: its decisions.
+template <int SZ>
+struct sc_node {
+    static PCL_DEVICE uint32_t run(const float* a, uint32_t fz, uint32_t& u)
+    {
+        constexpr uint32_t FULL = (SZ >= 32) ? 0xffffffffu : ((1u << SZ) - 1u);
+        constexpr int H = SZ / 2;
+        constexpr uint32_t HALF = (1u << H) - 1u;
+        if ((fz & FULL) == FULL) { u = 0; return 0; }          // rate-0 subtree: nothing to compute
+        float t[H];
+        uint32_t ul = 0, ur = 0, cl = 0;
+        if ((fz & HALF) != HALF) {
+#pragma unroll
+            for (int k = 0; k < H; k++) t[k] = pcl_math<float>::f(a[k], a[k + H]);
+            cl = sc_node<H>::run(t, fz & HALF, ul);
+        }
+#pragma unroll
+        for (int k = 0; k < H; k++) t[k] = sc_g(a[k], a[k + H], cl << (31 - k));
+        const uint32_t cr = sc_node<H>::run(t, (fz >> H) & HALF, ur);
+        u = ul | (ur << H);
+        return (cl ^ cr) | (cr << H);
+    }
+};
+template <>
+struct sc_node<1> {
+    static PCL_DEVICE uint32_t run(const float* a, uint32_t fz, uint32_t& u)
+    {
+        u = (fz & 1u) ? 0u : ((a[0] < 0.0f) ? 1u : 0u);        // decoder.py:58-66
+        return u;
+    }
+};
+
+// N = 256: eight nodes of 32 leaves.  b1 / b2 / b3: left arrays of levels 1 / 2 / 3 (128 / 64 / 32 bits).
+__global__ void __launch_bounds__(256) polar_sc256_kernel(PolarScParams P)
+{
+    constexpr int N = 256;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(P.next, 1ull) - P.ticket_base;
+        tk = pcl_shfl_u64(tk, 0);
+        const int64_t f0 = (int64_t)tk * 32;
+        if (f0 >= P.F) break;
+        const int64_t f = f0 + lane;
+        const bool valid = f < P.F;
+        const float* y = P.llr + (valid ? f : f0) * N;
+        uint32_t b1[4] = {0, 0, 0, 0}, b2[2] = {0, 0}, b3 = 0;
+#pragma unroll 1
+        for (int sb = 0; sb < 8; sb++) {
+            const uint32_t fz = P.frozen_words[sb];
+            uint32_t u = 0, c = 0;
+            if (fz != 0xffffffffu) {
+                const int bit1 = sb >> 2, bit2 = (sb >> 1) & 1, bit3 = sb & 1;
+                float R[32];
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    // element k of level 3 <- channel values 8 br5(k) .. + 7 (pairs (0,1) (2,3) (4,5) (6,7) are the
+                    // level-1 elements k, k + 64, k + 32, k + 96)
+                    const int br = ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+                    const float4 v0 = *reinterpret_cast<const float4*>(y + 8 * br);
+                    const float4 v1 = *reinterpret_cast<const float4*>(y + 8 * br + 4);
+                    float p01, p23, p45, p67, q0, q1;
+                    if (bit1) {
+                        p01 = sc_g(v0.x, v0.y, b1[0] << (31 - k));
+                        p23 = sc_g(v0.z, v0.w, b1[2] << (31 - k));
+                        p45 = sc_g(v1.x, v1.y, b1[1] << (31 - k));
+                        p67 = sc_g(v1.z, v1.w, b1[3] << (31 - k));
+                    } else {
+                        p01 = pcl_math<float>::f(v0.x, v0.y);
+                        p23 = pcl_math<float>::f(v0.z, v0.w);
+                        p45 = pcl_math<float>::f(v1.x, v1.y);
+                        p67 = pcl_math<float>::f(v1.z, v1.w);
+                    }
+                    if (bit2) {
+                        q0 = sc_g(p01, p23, b2[0] << (31 - k));
+                        q1 = sc_g(p45, p67, b2[1] << (31 - k));
+                    } else {
+                        q0 = pcl_math<float>::f(p01, p23);
+                        q1 = pcl_math<float>::f(p45, p67);
+                    }
+                    R[k] = bit3 ? sc_g(q0, q1, b3 << (31 - k)) : pcl_math<float>::f(q0, q1);
+                }
+                c = sc_node<32>::run(R, fz, u);
+            }
+            if (valid) P.uwords[f * (N / 32) + sb] = u;
+            // fold the node's partial sums upwards (decoder.py:96-115): a left child parks its word, a right
+            // child combines with its parked sibling and hands the pair on
+            if ((sb & 1) == 0) {
+                b3 = c;
+            } else {
+                const uint32_t x0 = b3 ^ c, x1 = c;                       // level-2 node: 64 bits
+                if ((sb & 2) == 0) {
+                    b2[0] = x0; b2[1] = x1;
+                } else if (sb == 3) {                                     // level-1 left node: 128 bits
+                    b1[0] = b2[0] ^ x0; b1[1] = b2[1] ^ x1; b1[2] = x0; b1[3] = x1;
+                }
+            }
+        }
+    }
+}
+
+// u words (decode-step order) -> K information bits per frame, ascending reference index (decoder.py:70-71)
+__global__ void __launch_bounds__(256) polar_sc_extract_kernel(const uint32_t* uwords, const uint16_t* info_pos, int64_t F,
+                                                               int NW, int K, uint8_t* bits)
+{
+    const int64_t total = F * (int64_t)K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / K;
+        const int k = (int)(i - f * K);
+        const int pos = info_pos[k];
+        bits[i] = (uint8_t)((uwords[f * NW + (pos >> 5)] >> (pos & 31)) & 1u);
+    }
+}

@@ -534,6 +534,9 @@ PCL_DEVICE void pcl_level_s2t(uint32_t tdst, const float* src, uint32_t smf)
 #ifndef PCL_POLAR_MINB
 #define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for (80 regs)
 #endif
+#ifndef PCL_POLAR_TM_GROUP
+#define PCL_POLAR_TM_GROUP 2      // warps that pull a chunk of frames together and stay in step (2: 10.59, 4: 10.47 Gbps)
+#endif
 #ifndef PCL_POLAR_TM_THREADS
 #define PCL_POLAR_TM_THREADS 640   // TM variant: ONE block per SM, 20 warps = 5 groups of 4 (96 registers; 768 / 80 is 7 % slower)
 #endif
@@ -580,7 +583,7 @@ polar_scl_fast_kernel(PolarParams<real> P)
     // Groups of 4 warps pull chunks of 4 FPW frames from a ticket counter and meet at their own
     // named barrier (the whole-block barrier of the other variant would couple all 24 warps).
     uint32_t tL4 = 0, tL6 = 0;
-    const int grp = warp >> 2, gw = warp & 3;
+    const int grp = warp / PCL_POLAR_TM_GROUP, gw = warp % PCL_POLAR_TM_GROUP;
     uint32_t* hdr = (uint32_t*)pcl_dyn_smem();    // [0] TMEM base, [4 + 4 g + 2 k ..] ticket of group g, parity k (64 bit)
     if (TM) {
         if (warp == 0) pcl_tmem_alloc_all(hdr);
@@ -588,7 +591,7 @@ polar_scl_fast_kernel(PolarParams<real> P)
         __syncthreads();
         pcl_tmem_fence_after();
         const int tmw = (PCL_TMEM_COLS / ((wpb + 3) >> 2)) & ~15;
-        tL4 = pcl_tmem_addr(hdr[0], warp, grp * tmw);
+        tL4 = pcl_tmem_addr(hdr[0], warp, (warp >> 2) * tmw);
         tL6 = tL4 + 64;
     }
 
@@ -602,8 +605,8 @@ polar_scl_fast_kernel(PolarParams<real> P)
         if (TM) {
             unsigned long long* tk = (unsigned long long*)(hdr + 4) + 2 * grp + (pass & 1);
             if (gw == 0 && lane == 0) *tk = atomicAdd(P.next, 1ull) - P.ticket_base;
-            pcl_named_barrier(1 + grp, 128);
-            fbase = (int64_t)(*(volatile unsigned long long*)tk) * (4 * FPW);
+            pcl_named_barrier(1 + grp, 32 * PCL_POLAR_TM_GROUP);
+            fbase = (int64_t)(*(volatile unsigned long long*)tk) * (PCL_POLAR_TM_GROUP * FPW);
             if (fbase >= P.F) break;
         } else {
             if (pass) fbase += (int64_t)gridDim.x * wpb * FPW;
@@ -870,6 +873,20 @@ polar_scl_fast_kernel(PolarParams<real> P)
                 if (LP == 1) {
                     u = ((fz8 >> j) & 1u) ? 0u : (hard ? 1u : 0u);
                     if (P.want_pm) pm -= (double)(sp + ((u != (uint32_t)hard) ? ax : (real)0));
+#if !defined(PCL_NO_FROZEN_PAIR)
+                } else if ((j & 1) == 0 && ((fz8 >> j) & 3u) == 3u && P.dbg_leaf == nullptr) {
+                    // Frozen pair (2 j, 2 j + 1): the right leaf needs no decision of the left one
+                    // (u = 0: x1 = R1[0] + R1[1]), so both penalties are evaluated side by side and the
+                    // loop moves on by two leaves; same operations in the same order as leaf by leaf.
+                    real x1 = R1[0] + R1[1];
+                    if (!act) x1 = (real)0;
+                    const real ax1 = fabs(x1);
+                    const real sp1 = pcl_fast<real>::softplus_neg_abs(ax1);
+                    pm -= (double)(sp + (hard ? ax : (real)0));
+                    pm -= (double)(sp1 + (!(x1 >= (real)0) ? ax1 : (real)0));
+                    small &= ~(1u << 30);
+                    j++;
+#endif
                 } else if ((fz8 >> j) & 1u) {
                     pm -= (double)(sp + (hard ? ax : (real)0));    // DEAD absorbs the penalty
                 } else {
