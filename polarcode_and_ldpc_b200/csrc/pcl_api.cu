@@ -471,11 +471,21 @@ static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    const int wpb = 8;
+    const int wpb = PCL_SC256_WPB;
+    const int smem = wpb * 32 * PCL_SC256_ROW * 4;               // 32 padded frame rows per warp
+    const int bps = std::max(1, di.smem_per_sm / (smem + 1024));
     const int64_t warps_needed = (F + 31) / 32;
-    const int grid = (int)std::min<int64_t>((warps_needed + wpb - 1) / wpb, (int64_t)di.sms * 2);
+    const int grid = (int)std::min<int64_t>((warps_needed + wpb - 1) / wpb, (int64_t)di.sms * bps);
     h->last_grid = grid;
-    PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, 0, stream, P);
+#ifndef PCL_EMU
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(polar_sc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaFuncSetAttribute(polar_sc256_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+#endif
+    PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, smem, stream, P);
     CUDA_TRY(cudaGetLastError());
     h->tickets[stage] += (unsigned long long)warps_needed + (unsigned long long)grid * wpb;
 #ifdef PCL_EMU

@@ -18,6 +18,7 @@
 // exactly as decoder.py:58-66, :121-144 -- in fp32; the fp64 validation build keeps the list kernel.
 #pragma once
 #include "pcl_common.cuh"
+#include "pcl_tmem.cuh"
 
 struct PolarScParams {
     const float* llr;               // [F][N] channel LLRs, reference index order
@@ -67,10 +68,18 @@ struct sc_node<1> {
 };
 
 // N = 256: eight nodes of 32 leaves.  b1 / b2 / b3: left arrays of levels 1 / 2 / 3 (128 / 64 / 32 bits).
-__global__ void __launch_bounds__(256) polar_sc256_kernel(PolarScParams P)
+// A lane reading its own frame straight from global memory touches 32 different lines per load
+// instruction (65 Gbps, L1 wavefront bound); instead the warp copies its 32 frames ONCE, coalesced
+// (cp.async, 512 contiguous bytes per instruction), into shared-memory rows of N + 4 floats -- the
+// 16-byte pad makes the lanes' 16-byte reads of their own rows conflict free -- and every later
+// visit of level 3 reads the channel from there.
+#define PCL_SC256_ROW 260
+#define PCL_SC256_WPB 3
+__global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc256_kernel(PolarScParams P)
 {
     constexpr int N = 256;
     const int lane = threadIdx.x & 31;
+    float* rows = (float*)pcl_dyn_smem() + (size_t)(threadIdx.x >> 5) * 32 * PCL_SC256_ROW;
     for (;;) {
         unsigned long long tk = 0;
         if (lane == 0) tk = atomicAdd(P.next, 1ull) - P.ticket_base;
@@ -79,7 +88,16 @@ __global__ void __launch_bounds__(256) polar_sc256_kernel(PolarScParams P)
         if (f0 >= P.F) break;
         const int64_t f = f0 + lane;
         const bool valid = f < P.F;
-        const float* y = P.llr + (valid ? f : f0) * N;
+        __syncwarp();                                            // the previous pass has read its rows
+#pragma unroll 4
+        for (int r = 0; r < 64; r++) {                           // frame r / 2, half r % 2: 512 contiguous bytes
+            const int64_t fr = (f0 + (r >> 1) < P.F) ? f0 + (r >> 1) : f0;
+            pcl_cp_async16(rows + (r >> 1) * PCL_SC256_ROW + (r & 1) * 128 + 4 * lane, P.llr + fr * N + (r & 1) * 128 + 4 * lane);
+        }
+        pcl_cp_async_commit();
+        pcl_cp_async_wait<0>();
+        __syncwarp();
+        const float* y = rows + lane * PCL_SC256_ROW;
         uint32_t b1[4] = {0, 0, 0, 0}, b2[2] = {0, 0}, b3 = 0;
 #pragma unroll 1
         for (int sb = 0; sb < 8; sb++) {
