@@ -65,11 +65,28 @@ PCL_DEVICE float pcl_rcpf(float x)
 #endif
 }
 
+PCL_DEVICE float pcl_lg2f(float x)
+{
+#ifdef PCL_EMU
+    return log2f(x);
+#else
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+
+#ifndef PCL_SOFTPLUS_LG2
+#define PCL_SOFTPLUS_LG2 0
+#endif
 template <typename real> struct pcl_fast;
 template <> struct pcl_fast<float> {
     static PCL_DEVICE float softplus_neg_abs(float ax)
     {
         const float u = pcl_ex2f(ax * -1.4426950408889634f);      // exp(-|x|) in (0, 1]
+#if PCL_SOFTPLUS_LG2
+        return pcl_lg2f(1.0f + u) * 0.6931471805599453f;          // two MUFU ops, 5 instructions
+#endif
         const float s = u * pcl_rcpf(2.0f + u);                   // log1p(u) = 2 atanh(s), s <= 1/3
         const float s2 = s * s;
         float pl = fmaf(s2, 0.07692308f, 0.09090909f);
@@ -531,6 +548,12 @@ PCL_DEVICE void pcl_level_s2t(uint32_t tdst, const float* src, uint32_t smf)
 #ifndef PCL_PRUNE_QUICK
 #define PCL_PRUNE_QUICK 1
 #endif
+#ifndef PCL_LEAF_V2
+#define PCL_LEAF_V2 1         // 32-bit quick test for in-place survivors, lean in-place update
+#endif
+#ifndef PCL_FROZEN_BLOCK
+#define PCL_FROZEN_BLOCK 1    // an all-frozen block of 8 leaves as straight-line code (no leaf loop)
+#endif
 #ifndef PCL_POLAR_MINB
 #define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for (80 regs)
 #endif
@@ -833,6 +856,35 @@ polar_scl_fast_kernel(PolarParams<real> P)
             // all borrowed source arrays have been read: order before later overwrites
             __syncwarp();
 
+            uint32_t c4hi = 0;                    // partial sums of leaves 4 .. 7 (size-4 field of the upper half)
+            if (PCL_FROZEN_BLOCK && !EXACT && LP > 1 && fz8 == 0xffu && P.dbg_leaf == nullptr) {
+                // ---- all-frozen block (46 of the 128 blocks of the headline code): no decisions, every
+                // g is a plain sum, so the 8 leaf LLRs are one straight-line butterfly and the 8 penalties
+                // are independent chains; added to the metric in leaf order (same sums as leaf by leaf).
+                real xs[8];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    real H[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) H[t] = h ? R3[t] + R3[t + 4] : pcl_math<real>::f(R3[t], R3[t + 4]);
+                    const real c0 = pcl_math<real>::f(H[0], H[2]), c1 = pcl_math<real>::f(H[1], H[3]);
+                    const real d0 = H[0] + H[2], d1 = H[1] + H[3];
+                    xs[4 * h + 0] = pcl_math<real>::f(c0, c1);
+                    xs[4 * h + 1] = c0 + c1;
+                    xs[4 * h + 2] = pcl_math<real>::f(d0, d1);
+                    xs[4 * h + 3] = d0 + d1;
+                }
+                double pmn = pm;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const real ax = fabs(xs[t]);
+                    const real pen = pcl_fast<real>::softplus_neg_abs(ax) + (!(xs[t] >= (real)0) ? ax : (real)0);
+                    pmn -= (double)pen;
+                }
+                pm = act ? pmn : pm;              // an inactive slot keeps DEAD whatever its registers hold
+                small &= ~(127u << 24);           // fields of sizes 4, 2, 1: all zero
+                ulast = 0;
+            } else {
             // ---- the 8 leaves of the block (rolled: the body must stay I-cache resident) ----
             real R2[4], R1[2];
 #pragma unroll
@@ -911,9 +963,22 @@ polar_scl_fast_kernel(PolarParams<real> P)
                         // Reliable bit on a full list (the common case): the likely keys are still in
                         // slot order and every unlikely key lies below the last of them, so the ranks
                         // are the slots themselves -- two shuffled compares instead of the ranking.
+#if PCL_LEAF_V2
+                        // Decided on the HIGH words alone (sign, exponent, 20 mantissa bits): every key is
+                        // negative (at most one likely key of a frame can be +0, and then its word is the
+                        // smallest), so a strictly larger unsigned high word means a strictly smaller key.
+                        // Equal high words say nothing: the list takes the full ranking below, which gives
+                        // the same survivors and slots.
+                        const uint32_t ha = (uint32_t)((uint64_t)__double_as_longlong(ka) >> 32);
+                        const uint32_t hb = (uint32_t)((uint64_t)__double_as_longlong(kb) >> 32);
+                        const uint32_t ha_prev = __shfl_up_sync(PCL_FULL_MASK, ha, 1, LP);
+                        const uint32_t ha_last = __shfl_sync(PCL_FULL_MASK, ha, cbase + ns - 1);
+                        in_place = __all_sync(PCL_FULL_MASK, p >= ns || ((p == 0 || ha > ha_prev) && hb > ha_last));
+#else
                         const double ka_prev = pcl_shfl_f64(ka, p == 0 ? lane : lane - 1);
                         const double ka_last = pcl_shfl_f64(ka, cbase + ns - 1);
                         in_place = __all_sync(PCL_FULL_MASK, p >= ns || ((p == 0 || ka < ka_prev) && kb < ka_last));
+#endif
                     }
                     if (!in_place) {
                     double2 kv;
@@ -967,8 +1032,13 @@ polar_scl_fast_kernel(PolarParams<real> P)
                     }
                     nact = ns;
                     if (in_place) {
+#if PCL_LEAF_V2
+                        // only reached on a full list: ns == nact, nobody's `act` changes, slots p >= ns stay DEAD
+                        if (p < ns) pm = ka;
+#else
                         act = (p < ns) && valid;
                         pm = (p < ns) ? ka : DEAD;
+#endif
                         u = hard ? 1u : 0u;
                     } else {
                         if (EXACT) {
@@ -1022,50 +1092,55 @@ polar_scl_fast_kernel(PolarParams<real> P)
                         const uint32_t c4 = (((small >> 28) & 3u) ^ c2) | (c2 << 2);
                         if (j == 3) {
                             small = (small & ~(15u << 24)) | (c4 << 24);
-                        } else if (blk == NB - 1) {
-                            ulast = u;               // last leaf: the fields stay as they are
                         } else {
-                            // block complete: fold upwards while the node is a right child
-                            uint32_t c = (((small >> 24) & 15u) ^ c4) | (c4 << 4);
-                            int s = 8, tt = blk;
-                            while ((tt & 1) && s < 32) {
-                                const uint32_t left = pcl_bfe(small, 32 - 2 * s, s);
-                                c = (left ^ c) | (c << s);
-                                s <<= 1;
-                                tt >>= 1;
-                            }
-                            if (!(tt & 1)) {
-                                if (s < 32) {
-                                    small = pcl_bfi(small, c, 32 - 2 * s, s);
-                                } else {
-                                    const int d = n - 5;
-                                    if (act) {
-                                        bw[32 * ((N >> 5) - (N >> (d + 4))) + lane] = c;
-                                        ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
-                                    }
-                                    __syncwarp();
-                                }
-                            } else {
-                                const int cto = __ffs(~(i0 + j)) - 1;
-                                const int d = n - cto;
-                                const int Wd = N >> (d + 5);
-                                uint32_t* dest = bw + 32 * ((N >> 5) - (N >> (d + 4)));
-                                if (act) dest[(Wd - 1) * 32 + lane] = c;
-                                __syncwarp();
-                                for (int l = n - 5; l > d; l--) {
-                                    const int w = N >> (l + 5);
-                                    const int ql = cbase + ((ptrB >> ((l - 1) * PB)) & (LP - 1));
-                                    const uint32_t* lsrc = bw + 32 * ((N >> 5) - (N >> (l + 4)));
-                                    if (act)
-                                        for (int jw = 0; jw < w; jw++)
-                                            dest[(Wd - 2 * w + jw) * 32 + lane] =
-                                                lsrc[jw * 32 + ql] ^ dest[(Wd - w + jw) * 32 + lane];
-                                    __syncwarp();
-                                }
-                                if (act) ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
-                            }
+                            c4hi = c4;               // leaf 7: the block is complete (folded below)
+                            ulast = u;
                         }
                     }
+                }
+            }
+            }
+
+            // ---- block complete: fold its 8 partial sums upwards while the node is a right child
+            // (the last block keeps its fields: the final u-word is assembled from them) -----------
+            if (blk != NB - 1) {
+                uint32_t c = (((small >> 24) & 15u) ^ c4hi) | (c4hi << 4);
+                int s = 8, tt = blk;
+                while ((tt & 1) && s < 32) {
+                    const uint32_t left = pcl_bfe(small, 32 - 2 * s, s);
+                    c = (left ^ c) | (c << s);
+                    s <<= 1;
+                    tt >>= 1;
+                }
+                if (!(tt & 1)) {
+                    if (s < 32) {
+                        small = pcl_bfi(small, c, 32 - 2 * s, s);
+                    } else {
+                        const int d = n - 5;
+                        if (act) {
+                            bw[32 * ((N >> 5) - (N >> (d + 4))) + lane] = c;
+                            ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    const int cto = __ffs(~(i0 + 7)) - 1;
+                    const int d = n - cto;
+                    const int Wd = N >> (d + 5);
+                    uint32_t* dest = bw + 32 * ((N >> 5) - (N >> (d + 4)));
+                    if (act) dest[(Wd - 1) * 32 + lane] = c;
+                    __syncwarp();
+                    for (int l = n - 5; l > d; l--) {
+                        const int w = N >> (l + 5);
+                        const int ql = cbase + ((ptrB >> ((l - 1) * PB)) & (LP - 1));
+                        const uint32_t* lsrc = bw + 32 * ((N >> 5) - (N >> (l + 4)));
+                        if (act)
+                            for (int jw = 0; jw < w; jw++)
+                                dest[(Wd - 2 * w + jw) * 32 + lane] =
+                                    lsrc[jw * 32 + ql] ^ dest[(Wd - w + jw) * 32 + lane];
+                        __syncwarp();
+                    }
+                    if (act) ptrB = (ptrB & ~((uint32_t)(LP - 1) << ((d - 1) * PB))) | ((uint32_t)p << ((d - 1) * PB));
                 }
             }
         }
