@@ -136,6 +136,8 @@ struct pcl_polar {
 #ifndef PCL_EMU
     HostPipe pipe;              // host-buffer pipeline (pcl_host_pipe.cuh)
 #endif
+    std::vector<uint8_t> frozen_copy;              // the caller's mask (twin creation)
+    pcl_polar* twin = nullptr;  // run-time-N handle for per-leaf dumps when this one has a compiled code length
 };
 
 static size_t real_size(int dtype) { return dtype == PCL_F64 ? 8 : 4; }
@@ -273,8 +275,17 @@ static int polar_occ(pcl_polar* h, int threads, int smem, int* bps)
 }
 #endif
 
+static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
+                             int crc_len, uint32_t crc_poly, int dtype, bool compiled_ok);
+
 extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
                                 int crc_len, uint32_t crc_poly, int dtype)
+{
+    return polar_create_impl(out, N, K, list_size, frozen_mask, crc_len, crc_poly, dtype, true);
+}
+
+static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
+                             int crc_len, uint32_t crc_poly, int dtype, bool compiled_ok)
 {
     if (!out || !frozen_mask) return fail(PCL_EINVAL, "null argument");
     // src/polar/decoder.py:17-18, :194-196
@@ -291,6 +302,7 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     if (nfree != K) return fail(PCL_EINVAL, "frozen mask leaves %d info positions, K=%d", nfree, K);
 
     pcl_polar* h = new pcl_polar();
+    h->frozen_copy.assign(frozen_mask, frozen_mask + N);
     h->N = N; h->n = n; h->K = K; h->L = list_size; h->dtype = dtype;
     h->crc_len = crc_len; h->crc_poly = crc_poly;
     int LP = 1;
@@ -319,7 +331,8 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
     // generic all-shared-memory kernel.  A configuration whose shared memory does not fit a block retries
     // with fewer warps per block (4, 2, 1) and then falls back to the next kernel in the list.
     const bool can_fast = n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 && env_int("PCL_POLAR_GENERIC", 0) == 0;
-    const bool can_tm = can_fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && env_int("PCL_POLAR_TM", 1) != 0 &&
+    const bool nl_ok = compiled_ok && env_int("PCL_POLAR_NL", 1) != 0;
+    const bool can_tm = can_fast && dtype == PCL_F32 && nl_ok && env_int("PCL_POLAR_TM", 1) != 0 &&
                         n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 0) != 0);
     int bps = 1;
     bool placed = false;
@@ -358,7 +371,7 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
             G = std::max(gmin, std::min(G, gmax));
             polar_layout(h->lay, N, K, list_size, LP, G, rsz, crc_len > 0, h->fast, h->fpw);
             // code lengths with log2 N and G compiled in (fp32 build; the validation build reads them at run time)
-            if (h->fast && dtype == PCL_F32 && env_int("PCL_POLAR_NL", 1) != 0 && polar_fast_variant_exists(LP, n, G, 0)) { h->NL = n; h->GL = G; }
+            if (h->fast && dtype == PCL_F32 && nl_ok && polar_fast_variant_exists(LP, n, G, 0)) { h->NL = n; h->GL = G; }
             int w = env_int("PCL_POLAR_WPB", 4);
             if (w < 1 || w > 4) w = 4;
             while (w > 1 && h->lay.warp_bytes * w > di.smem_per_block) w >>= 1;
@@ -418,6 +431,7 @@ extern "C" int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, 
 extern "C" void pcl_polar_destroy(pcl_polar_t* h)
 {
     if (!h) return;
+    if (h->twin) pcl_polar_destroy(h->twin);
     cudaFree(h->d_frozen_words);
     cudaFree(h->d_info_pos);
     for (int s = 0; s < PCL_NSTAGE; s++) {
@@ -506,6 +520,14 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
 {
     if (h->sc256 && pm_dev == nullptr && leaf_dev == nullptr && sizeof(real) == 4)
         return polar_sc256_decode(h, llr_dev, F, bits_dev, stream, stage);
+    if (leaf_dev != nullptr && h->fast && h->NL != 0) {
+        // per-leaf dumps are compiled into the run-time-N kernels only (same results bit for bit)
+        if (!h->twin) {
+            int rc = polar_create_impl(&h->twin, h->N, h->K, h->L, h->frozen_copy.data(), h->crc_len, h->crc_poly, h->dtype, false);
+            if (rc) return rc;
+        }
+        return polar_decode_impl<real>(h->twin, llr_dev, F, bits_dev, pm_dev, leaf_dev, parent_dev, h->twin->d_scratch[0], stream, 0);
+    }
     PolarParams<real> P;
     P.lay = h->lay;
     P.llr = (const real*)llr_dev;

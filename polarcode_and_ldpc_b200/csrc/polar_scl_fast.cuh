@@ -77,7 +77,7 @@ PCL_DEVICE float pcl_lg2f(float x)
 }
 
 #ifndef PCL_SOFTPLUS_LG2
-#define PCL_SOFTPLUS_LG2 0
+#define PCL_SOFTPLUS_LG2 1
 #endif
 template <typename real> struct pcl_fast;
 template <> struct pcl_fast<float> {
@@ -572,6 +572,10 @@ polar_scl_fast_kernel(PolarParams<real> P)
     constexpr int FPW = 32 / LP;                 // frames per warp
     constexpr int NC = 2 * LP;                   // prune candidates per frame
     constexpr bool EXACT = sizeof(real) == 8;
+    // per-leaf LLR / parent dumps (SCDecoder.L, the debug scripts) only in the run-time-N variants: a handle
+    // with a compiled code length keeps a run-time-N twin for those calls (pcl_api.cu), and the production
+    // leaf loop carries no test for them
+    constexpr bool DBG = (NL == 0);
     constexpr int FB = pcl_fast_frame_bytes(LP);
     const PolarLayout& Y = P.lay;
     const int n = NL ? NL : Y.n;
@@ -857,7 +861,7 @@ polar_scl_fast_kernel(PolarParams<real> P)
             __syncwarp();
 
             uint32_t c4hi = 0;                    // partial sums of leaves 4 .. 7 (size-4 field of the upper half)
-            if (PCL_FROZEN_BLOCK && !EXACT && LP > 1 && fz8 == 0xffu && P.dbg_leaf == nullptr) {
+            if (PCL_FROZEN_BLOCK && !EXACT && LP > 1 && fz8 == 0xffu && (!DBG || P.dbg_leaf == nullptr)) {
                 // ---- all-frozen block (46 of the 128 blocks of the headline code): no decisions, every
                 // g is a plain sum, so the 8 leaf LLRs are one straight-line butterfly and the 8 penalties
                 // are independent chains; added to the metric in leaf order (same sums as leaf by leaf).
@@ -925,8 +929,8 @@ polar_scl_fast_kernel(PolarParams<real> P)
                 if (LP == 1) {
                     u = ((fz8 >> j) & 1u) ? 0u : (hard ? 1u : 0u);
                     if (P.want_pm) pm -= (double)(sp + ((u != (uint32_t)hard) ? ax : (real)0));
-#if !defined(PCL_NO_FROZEN_PAIR)
-                } else if ((j & 1) == 0 && ((fz8 >> j) & 3u) == 3u && P.dbg_leaf == nullptr) {
+                } else if ((fz8 >> j) & 1u) {
+                    if ((j & 1) == 0 && ((fz8 >> j) & 3u) == 3u && (!DBG || P.dbg_leaf == nullptr)) {
                     // Frozen pair (2 j, 2 j + 1): the right leaf needs no decision of the left one
                     // (u = 0: x1 = R1[0] + R1[1]), so both penalties are evaluated side by side and the
                     // loop moves on by two leaves; same operations in the same order as leaf by leaf.
@@ -938,9 +942,9 @@ polar_scl_fast_kernel(PolarParams<real> P)
                     pm -= (double)(sp1 + (!(x1 >= (real)0) ? ax1 : (real)0));
                     small &= ~(1u << 30);
                     j++;
-#endif
-                } else if ((fz8 >> j) & 1u) {
+                    } else {
                     pm -= (double)(sp + (hard ? ax : (real)0));    // DEAD absorbs the penalty
+                    }
                 } else {
                     const int ns = (2 * nact < L) ? 2 * nact : L;
                     int ra = 0, rb = 0;
@@ -1076,7 +1080,7 @@ polar_scl_fast_kernel(PolarParams<real> P)
                         }
                     }
                 }
-                if (P.dbg_leaf != nullptr && valid) {
+                if (DBG && P.dbg_leaf != nullptr && valid) {
                     P.dbg_leaf[(f * N + i0 + j) * LP + p] = x;
                     P.dbg_parent[(f * N + i0 + j) * LP + p] = (uint8_t)parent;
                 }
