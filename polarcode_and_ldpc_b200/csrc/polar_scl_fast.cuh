@@ -540,6 +540,40 @@ PCL_DEVICE void pcl_level_s2t(uint32_t tdst, const float* src, uint32_t smf)
     pcl_tmem_wait_st();
 }
 
+// SC (list size 1) without a metric: the 8 leaves of a block as one unrolled recursion -- no leaf loop, no
+// softplus, a frozen subtree costs nothing (same rules as polar_sc.cuh: f, g, bit = [x < 0]).  Returns the
+// node's partial sums, u = its decisions.
+template <typename real, int SZ>
+struct pcl_sc_node {
+    static PCL_DEVICE uint32_t run(const real* a, uint32_t fz, uint32_t& u)
+    {
+        constexpr uint32_t FULL = (1u << SZ) - 1u;
+        constexpr int H = SZ / 2;
+        constexpr uint32_t HALF = (1u << H) - 1u;
+        if ((fz & FULL) == FULL) { u = 0; return 0; }
+        real t[H];
+        uint32_t ul = 0, ur = 0, cl = 0;
+        if ((fz & HALF) != HALF) {
+#pragma unroll
+            for (int k = 0; k < H; k++) t[k] = pcl_math<real>::f(a[k], a[k + H]);
+            cl = pcl_sc_node<real, H>::run(t, fz & HALF, ul);
+        }
+#pragma unroll
+        for (int k = 0; k < H; k++) t[k] = pcl_fast<real>::gs(a[k], a[k + H], cl << (31 - k));
+        const uint32_t cr = pcl_sc_node<real, H>::run(t, (fz >> H) & HALF, ur);
+        u = ul | (ur << H);
+        return (cl ^ cr) | (cr << H);
+    }
+};
+template <typename real>
+struct pcl_sc_node<real, 1> {
+    static PCL_DEVICE uint32_t run(const real* a, uint32_t fz, uint32_t& u)
+    {
+        u = (fz & 1u) ? 0u : (!(a[0] >= (real)0) ? 1u : 0u);     // decoder.py:58-66
+        return u;
+    }
+};
+
 // LP = list slots per frame (power of two); a warp decodes FPW = 32 / LP frames side by side.
 // NL = log2 N as a compile-time constant (0: read it from the layout), GL = G for that NL.
 #ifndef PCL_PRUNE_SHORTCUT
@@ -553,6 +587,9 @@ PCL_DEVICE void pcl_level_s2t(uint32_t tdst, const float* src, uint32_t smf)
 #endif
 #ifndef PCL_FROZEN_BLOCK
 #define PCL_FROZEN_BLOCK 1    // an all-frozen block of 8 leaves as straight-line code (no leaf loop)
+#endif
+#ifndef PCL_SC_BLOCK
+#define PCL_SC_BLOCK 1        // list size 1 without a metric: unrolled 8-leaf recursion instead of the leaf loop
 #endif
 #ifndef PCL_POLAR_MINB
 #define PCL_POLAR_MINB 6      // resident 128-thread blocks per SM the register allocation aims for (80 regs)
@@ -888,6 +925,15 @@ polar_scl_fast_kernel(PolarParams<real> P)
                 pm = act ? pmn : pm;              // an inactive slot keeps DEAD whatever its registers hold
                 small &= ~(127u << 24);           // fields of sizes 4, 2, 1: all zero
                 ulast = 0;
+            } else if (PCL_SC_BLOCK && LP == 1 && !P.want_pm && (!DBG || P.dbg_leaf == nullptr)) {
+                // ---- SC, bits only: the block as an unrolled recursion (pcl_sc_node) -----------------
+                uint32_t u8 = 0;
+                const uint32_t c8 = pcl_sc_node<real, 8>::run(R3, fz8, u8);
+                c4hi = c8 >> 4;
+                // fields as the leaf loop leaves them: size 4 = sums of leaves 0 .. 3, size 2 = (u4 ^ u5, u5), size 1 = u6
+                small = (small & ~(127u << 24)) | (((c8 ^ (c8 >> 4)) & 15u) << 24) |
+                        ((((u8 >> 4) ^ (u8 >> 5)) & 1u) << 28) | (((u8 >> 5) & 1u) << 29) | (((u8 >> 6) & 1u) << 30);
+                ulast = (u8 >> 7) & 1u;
             } else {
             // ---- the 8 leaves of the block (rolled: the body must stay I-cache resident) ----
             real R2[4], R1[2];

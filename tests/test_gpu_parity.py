@@ -196,6 +196,17 @@ def test_sc_n256_config1():
         assert np.array_equal(P.SCDecoder(N, K, frozen_bits=frozen, dtype=dt).decode_batch(llr), ref)
 
 
+@pytest.mark.parametrize("N,K", [(64, 20), (512, 300), (1024, 512), (2048, 1024)])
+def test_sc_bits_only_sizes(N, K):
+    """SC at other code lengths, bits only: the list kernel with L = 1 takes each block of 8 leaves as an
+    unrolled recursion (pcl_sc_node) instead of the leaf loop.  fp64 exact, fp32 identical frames."""
+    frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+    _, llr = _polar_frames(N, K, frozen, 3000, 1.0, N + K)
+    ref = oracle.polar_sc(N, frozen, llr, nthreads=8)
+    assert np.array_equal(P.SCDecoder(N, K, frozen_bits=frozen, dtype="float64").decode_batch(llr), ref)
+    assert int((P.SCDecoder(N, K, frozen_bits=frozen).decode_batch(llr) != ref).any(axis=1).sum()) == 0
+
+
 def _settled(H, llr, mode, kw, iters):
     """Frames whose reference decode (with early stop) converges within `iters` iterations."""
     kw2 = dict(kw, early_stop=True)
