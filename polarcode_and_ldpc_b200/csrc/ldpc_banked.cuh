@@ -22,6 +22,25 @@
 #pragma once
 #include "ldpc_bp.cuh"
 
+// Message words addressed by a 32-bit shared-space address + byte offset (the variable pass): the
+// offsets come packed from a table and one integer add per word forms the address.
+#ifdef PCL_EMU
+typedef unsigned char* pcl_saddr;
+PCL_DEVICE pcl_saddr pcl_saddr_of(void* p) { return (unsigned char*)p; }
+PCL_DEVICE float pcl_lds_f32(pcl_saddr a) { return *reinterpret_cast<const float*>(a); }
+PCL_DEVICE void pcl_sts_f32(pcl_saddr a, float v) { *reinterpret_cast<float*>(a) = v; }
+#else
+typedef uint32_t pcl_saddr;
+PCL_DEVICE pcl_saddr pcl_saddr_of(void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PCL_DEVICE float pcl_lds_f32(pcl_saddr a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+PCL_DEVICE void pcl_sts_f32(pcl_saddr a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+#endif
+
 // PAIRED: the k-th message of the check at (R, lane) is word 64 (DC/2 R + k/2) + 2 lane + (k & 1):
 // the check pass moves two messages per 8-byte access (conflict free), an edge's bank becomes
 // 2 (lane % 16) + (k & 1), and the host search also decides which half of a check's edges sit
@@ -35,7 +54,11 @@ __global__ void __launch_bounds__(COOP ? 256 : 1024) ldpc_banked_kernel(LdpcPara
     const LdpcLayout& Y = P.lay;
     const int n = Y.n, nR = Y.nR, NP = Y.NP, NS = Y.NS;
     const int lane = threadIdx.x & 31;
+#ifdef PCL_LDPC_ONEWARP     // experiment: blocks of one warp (launch with PCL_LDPC_FAT=0 PCL_LDPC_WPB=1), constant shared-memory base
+    const int warp = COOP ? (threadIdx.x >> 5) : 0;
+#else
     const int warp = threadIdx.x >> 5;
+#endif
     constexpr bool coop = COOP != 0;
     const int T = coop ? (int)blockDim.x : 32;
     const int tid = coop ? (int)threadIdx.x : lane;
@@ -43,6 +66,7 @@ __global__ void __launch_bounds__(COOP ? 256 : 1024) ldpc_banked_kernel(LdpcPara
     unsigned char* wsm = pcl_dyn_smem() + (coop ? (size_t)0 : (size_t)warp * Y.warp_bytes);
     float* msg = (float*)(wsm + Y.off_msg);
     float* sllr = (float*)(wsm + Y.off_llr);
+    const pcl_saddr msg_s = pcl_saddr_of(msg);
     uint32_t* hard = (uint32_t*)(wsm + Y.off_hard);
     unsigned long long* ctl = (unsigned long long*)(wsm + Y.off_ctl);
     auto sync = [&]() {
@@ -145,24 +169,48 @@ __global__ void __launch_bounds__(COOP ? 256 : 1024) ldpc_banked_kernel(LdpcPara
             sync();
             // 2. variable nodes + 3. hard decision, in position space
             const bool want_hard = Y.early_stop || it == Y.max_iter - 1;
-            for (int vb = 32 * w0; vb < NP; vb += 32 * wstep) {
-                const int pi = vb + lane;
-                const unsigned long long pk = P.bpack[pi];
-                bool bit = false;
-                if ((pk >> 48) == 0) {
-                    const int ea = (int)(pk & 0xffffu), eb = (int)((pk >> 16) & 0xffffu), ec = (int)((pk >> 32) & 0xffffu);
-                    const float ma = msg[ea], mb = msg[eb], mc = msg[ec];
+            // (the pass exists in four compiled versions -- with / without hard decisions and the total-LLR
+            // dump -- so that the common one carries no per-position tests; table words of four positions
+            // are fetched ahead of the shared-memory accesses)
+            auto var_pass = [&](auto hard_c, auto total_c) {
+                constexpr bool HARD = decltype(hard_c)::value, TOTAL = decltype(total_c)::value;
+                // three byte offsets into the message array, 16 bits each
+                auto one = [&](int vb, unsigned long long pk) {
+                    const int pi = vb + lane;
+                    const uint32_t plo = (uint32_t)pk;
+                    const pcl_saddr pa = msg_s + (plo & 0xffffu), pb = msg_s + (plo >> 16), pc = msg_s + (uint32_t)(pk >> 32);
+                    const float ma = pcl_lds_f32(pa), mb = pcl_lds_f32(pb), mc = pcl_lds_f32(pc);
                     const float total = sllr[pi] + ((ma + mb) + mc);
-                    msg[ea] = total - ma;
-                    msg[eb] = total - mb;
-                    msg[ec] = total - mc;
-                    bit = (total <= 0.0f);
-                    if (P.total != nullptr) P.total[f * n + P.varof[pi]] = total * (MODE == 0 ? 0.6931471805599453f : 1.0f);
+                    pcl_sts_f32(pa, total - ma);
+                    pcl_sts_f32(pb, total - mb);
+                    pcl_sts_f32(pc, total - mc);
+                    if (TOTAL) {
+                        const int v = P.varof[pi];
+                        if (v != 0xffff) P.total[f * n + v] = total * (MODE == 0 ? 0.6931471805599453f : 1.0f);
+                    }
+                    if (HARD) {
+                        const unsigned bal = __ballot_sync(PCL_FULL_MASK, total <= 0.0f);
+                        if (lane == 0) hard[vb >> 5] = bal;
+                    }
+                };
+                const int step = 32 * wstep;
+                int vb = 32 * w0;
+                for (; vb + 3 * step < NP; vb += 4 * step) {
+                    const unsigned long long k0 = P.bpack[vb + lane], k1 = P.bpack[vb + step + lane],
+                                             k2 = P.bpack[vb + 2 * step + lane], k3 = P.bpack[vb + 3 * step + lane];
+                    one(vb, k0);
+                    one(vb + step, k1);
+                    one(vb + 2 * step, k2);
+                    one(vb + 3 * step, k3);
                 }
-                if (want_hard) {
-                    const unsigned bal = __ballot_sync(PCL_FULL_MASK, bit);
-                    if (lane == 0) hard[vb >> 5] = bal;
-                }
+                for (; vb < NP; vb += step) one(vb, P.bpack[vb + lane]);
+            };
+            if (P.total != nullptr) {
+                if (want_hard) var_pass(pcl_true(), pcl_true());
+                else var_pass(pcl_false(), pcl_true());
+            } else {
+                if (want_hard) var_pass(pcl_true(), pcl_false());
+                else var_pass(pcl_false(), pcl_false());
             }
             sync();
             // 4. syndrome early stop

@@ -49,7 +49,7 @@ struct LdpcParams {
     const int32_t* vptr;        // [n+1]
     const uint16_t* vperm;      // [E] edge ids, variable-major
     const unsigned long long* vpack;  // REG: per variable, its 3 edge ids packed 16 bits each
-    const unsigned long long* bpack;  // banked: per variable position, its 3 slots (bits 48.. set: hole)
+    const unsigned long long* bpack;  // banked: per variable position, the byte offsets of its 3 message words (16 bits each)
     const uint16_t* varof;      // banked: variable at position pi (0xffff: hole)
     const uint16_t* posof;      // banked: position of variable v
     const uint16_t* cpos;       // banked: variable position behind slot s (0xffff: hole)
@@ -207,6 +207,10 @@ PCL_DEVICE float2 pcl_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 template <int DMAX>
 PCL_DEVICE void cn_bp_core2(const uint32_t* xa, const uint32_t* xb, float* outa, float* outb)
 {
+    // The first and last steps of both recurrences meet the identity pair (E, O) = (1, 0): those
+    // multiply-adds are written out by hand (x * 1 + 0 is exact, so the results are the same bits;
+    // the compiler may not drop them itself because 0 * inf is not 0).
+    static_assert(DMAX >= 4, "pair rule is written for check degree >= 4");
     const float UMIN = 5.00000250000125e-07f;
     float2 u[DMAX];
     uint32_t sa = 0, sb = 0;
@@ -217,28 +221,46 @@ PCL_DEVICE void cn_bp_core2(const uint32_t* xa, const uint32_t* xb, float* outa,
         sa ^= xa[j];
         sb ^= xb[j];
     }
-    float2 se[DMAX + 1], so[DMAX + 1];
-    se[DMAX].x = se[DMAX].y = 1.0f;
-    so[DMAX].x = so[DMAX].y = 0.0f;
+    float2 one;
+    one.x = one.y = 1.0f;
+    // suffix pairs over edges j .. DMAX-1; (se, so)[DMAX-1] = (1, u[DMAX-1])
+    float2 se[DMAX], so[DMAX];
+    se[DMAX - 1] = one;
+    so[DMAX - 1] = u[DMAX - 1];
 #pragma unroll
-    for (int j = DMAX - 1; j >= 1; j--) {
+    for (int j = DMAX - 2; j >= 1; j--) {
         se[j] = pcl_fma2(u[j], so[j + 1], se[j + 1]);
         so[j] = pcl_fma2(u[j], se[j + 1], so[j + 1]);
     }
-    float2 pe, po;
-    pe.x = pe.y = 1.0f;
-    po.x = po.y = 0.0f;
+    float2 pe = one, po = u[0];                  // prefix pair over edges 0 .. i-1 (i >= 1)
 #pragma unroll
     for (int i = 0; i < DMAX; i++) {
-        const float2 E = pcl_fma2(po, so[i + 1], pcl_mul2(pe, se[i + 1]));
-        const float2 O = pcl_fma2(po, se[i + 1], pcl_mul2(pe, so[i + 1]));
+        float2 E, O;
+        if (i == 0) {                            // no prefix
+            E = se[1];
+            O = so[1];
+        } else if (i == DMAX - 1) {              // no suffix
+            E = pe;
+            O = po;
+        } else if (i == 1) {                     // prefix = (1, u0)
+            E = pcl_fma2(po, so[2], se[2]);
+            O = pcl_fma2(po, se[2], so[2]);
+        } else if (i == DMAX - 2) {              // suffix = (1, u[DMAX-1])
+            E = pcl_fma2(po, so[i + 1], pe);
+            O = pcl_fma2(pe, so[i + 1], po);
+        } else {
+            E = pcl_fma2(po, so[i + 1], pcl_mul2(pe, se[i + 1]));
+            O = pcl_fma2(po, se[i + 1], pcl_mul2(pe, so[i + 1]));
+        }
         const float inv = pcl_rcp(O.x * O.y);
         const float ra = (E.x * O.y) * inv, rb = (E.y * O.x) * inv;
         outa[i] = __uint_as_float(__float_as_uint(pcl_lg2(ra)) | ((sa ^ xa[i]) & 0x80000000u));
         outb[i] = __uint_as_float(__float_as_uint(pcl_lg2(rb)) | ((sb ^ xb[i]) & 0x80000000u));
-        const float2 npe = pcl_fma2(u[i], po, pe);
-        po = pcl_fma2(u[i], pe, po);
-        pe = npe;
+        if (i >= 1 && i < DMAX - 1) {
+            const float2 npe = pcl_fma2(u[i], po, pe);
+            po = pcl_fma2(u[i], pe, po);
+            pe = npe;
+        }
     }
 }
 

@@ -789,8 +789,47 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
             }
         }
         if (have) {
-            Y.banked = 1; Y.nR = bl.nR; Y.NP = bl.NP; Y.NS = bl.NS; Y.paired = paired ? 1 : 0;
+            Y.banked = 1; Y.nR = bl.nR; Y.NP = bl.NP; Y.paired = paired ? 1 : 0;
             h->banked_residual = bl.residual;
+            // Device form of the per-position table: BYTE offsets of the three message words (the variable
+            // pass adds them to the frame's base, no shifts).  An empty position points at words of an EMPTY
+            // check seat instead of carrying a flag the kernel would have to branch on: such words start at
+            // zero, the check rule maps six zeros to six zeros, and a position whose channel value is zero
+            // writes zeros back, so they stay zero for the whole decode.  (A (3, 6) code with empty positions
+            // always has an empty seat: n = 2 m.)  The word is taken from a bank the fetch leaves free when
+            // there is one; otherwise that fetch costs one more wavefront.
+            Y.NS = bl.NS;
+            std::vector<int> zero_words;
+            for (int sidx = 0; sidx < bl.NS; sidx++)
+                if (bl.cpos[sidx] == 0xffff) zero_words.push_back(sidx);
+            bool holes = false;
+            for (int pi = 0; pi < bl.NP; pi++) holes = holes || (bl.bpack[pi] >> 48) != 0;
+            if ((holes && zero_words.empty()) || 4 * Y.NS > 65535) have = false;
+            for (int r = 0; r < bl.NP / 32 && have && holes; r++)
+                for (int j = 0; j < 3; j++) {
+                    bool used[32] = {};
+                    for (int l = 0; l < 32; l++) {
+                        const unsigned long long pk = bl.bpack[32 * r + l];
+                        if ((pk >> 48) == 0) used[((pk >> (16 * j)) & 0xffffu) & 31] = true;
+                    }
+                    for (int l = 0; l < 32; l++) {
+                        unsigned long long& pk = bl.bpack[32 * r + l];
+                        if ((pk >> 48) == 0) continue;
+                        int pick = zero_words[0];
+                        for (int z : zero_words)
+                            if (!used[z & 31]) { pick = z; break; }
+                        used[pick & 31] = true;
+                        pk = (pk & ~(0xffffull << (16 * j))) | ((unsigned long long)pick << (16 * j));
+                    }
+                }
+            if (have) {
+                for (auto& pk : bl.bpack) {
+                    const unsigned long long a = pk & 0xffffu, b = (pk >> 16) & 0xffffu, c = (pk >> 32) & 0xffffu;
+                    pk = (4 * a) | ((4 * b) << 16) | ((4 * c) << 32);
+                }
+            } else {
+                Y.banked = 0; Y.nR = 0; Y.NP = 0; Y.NS = 0; Y.paired = 0;
+            }
         }
     }
     int off = 0;
