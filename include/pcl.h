@@ -56,6 +56,7 @@ int pcl_device_count(void);
  * equal the number of zeros.  list_size 1 with want_metric 0 is the SC decoder.
  * crc_len 0 disables CRC-aided selection (the reference never applies it,
  * decoder.py:259); otherwise crc_poly/crc_len follow src/polar/utils.py:128-163.
+ * Limits (PCL_EUNSUPPORTED beyond): N <= 8192, list_size <= 1024.
  */
 int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
                      int crc_len, uint32_t crc_poly, int dtype);
@@ -92,7 +93,9 @@ int pcl_polar_lp(const pcl_polar_t* h);
  * dynamic shared memory, number of tree levels kept in the L2 scratch, and the kernel in use:
  * 0 = generic kernel, 1 = register-resident-bottom kernel (a lane owns a path, 32 / LP frames
  * per warp), 2 = the same with log2 N and the level split compiled in as constants, 3 = the
- * one-block-per-SM variant with the mid tree levels in tensor / shared memory. */
+ * one-block-per-SM variant with the mid tree levels in tensor / shared memory, 4 = the
+ * register-resident SC kernel for N = 256, 5 = the block-per-frame kernel for list sizes 33 .. 1024
+ * (any list_size >= 1 is what the reference accepts, src/polar/decoder.py:194-196). */
 int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
                           int* fast);
 

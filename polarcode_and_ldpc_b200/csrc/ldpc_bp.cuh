@@ -298,6 +298,63 @@ PCL_DEVICE void cn_bp_f32(float* msg, int d)
     }
 }
 
+// ---- check node of ANY degree, in place, no per-thread arrays (checks wider than 32 edges) ----
+// Phase 1 replaces every message by its transformed value (fp64: the clipped tanh; fp32: u with the
+// sign of the message); phase 2 walks the edges in order with the running PREFIX in registers and
+// folds the not-yet-overwritten entries behind edge i onto it.  fp64: exactly the reference's
+// left-to-right product that skips i (decoder.py:84-90), O(d^2) multiplies; fp32: the even / odd pair.
+PCL_DEVICE void cn_bp_loop(double* msg, int d)
+{
+    for (int j = 0; j < d; j++) {
+        double v = tanh(msg[j] / 2.0);
+        msg[j] = fmin(fmax(v, -0.999999), 0.999999);
+    }
+    double pre = 1.0;
+    bool has_pre = false;
+    for (int i = 0; i < d; i++) {
+        double pr = pre;
+        bool first = !has_pre;
+        for (int j = i + 1; j < d; j++) {
+            if (first) { pr = msg[j]; first = false; } else pr = pr * msg[j];
+        }
+        if (first) pr = 1.0;                                   // degree-1 check: empty product
+        const double ti = msg[i];
+        pr = fmin(fmax(pr, -0.999999), 0.999999);
+        double o = 2.0 * atanh(pr);
+        if (o != o) o = 0.0;
+        msg[i] = o;
+        if (has_pre) pre = pre * ti; else { pre = ti; has_pre = true; }
+    }
+}
+PCL_DEVICE void cn_bp_loop(float* msg, int d)
+{
+    const float UMIN = 5.00000250000125e-07f, RMAX = 1999999.0f;
+    uint32_t sall = 0;
+    for (int j = 0; j < d; j++) {
+        const uint32_t xb = __float_as_uint(msg[j]);
+        const float u = fmaxf(pcl_ex2(fabsf(msg[j]) * -1.4426950408889634f), UMIN);
+        sall ^= xb;
+        msg[j] = __uint_as_float(__float_as_uint(u) | (xb & 0x80000000u));
+    }
+    float pe = 1.0f, po = 0.0f;
+    for (int i = 0; i < d; i++) {
+        float e = pe, o = po;
+        for (int j = i + 1; j < d; j++) {
+            const float u = fabsf(msg[j]);
+            const float ne = fmaf(u, o, e);
+            o = fmaf(u, e, o);
+            e = ne;
+        }
+        const uint32_t xi = __float_as_uint(msg[i]);
+        const float ui = fabsf(msg[i]);
+        const float mag = 0.6931471805599453f * pcl_lg2(fminf(e * pcl_rcp(o), RMAX));
+        msg[i] = __uint_as_float(__float_as_uint(mag) | ((sall ^ xi) & 0x80000000u));
+        const float npe = fmaf(ui, po, pe);
+        po = fmaf(ui, pe, po);
+        pe = npe;
+    }
+}
+
 // ---- check node, Min-Sum (decoder.py:257-287), any degree, in place -------------
 template <typename real>
 PCL_DEVICE void cn_ms(real* msg, int d, real norm)
@@ -466,11 +523,12 @@ __global__ void __launch_bounds__(256) ldpc_decode_kernel(LdpcParams<real> P)
             for (int c = tid; c < m; c += T) {
                 const int e0 = REG ? c * DMAX : P.cptr[c];
                 const int d = REG ? DMAX : P.cptr[c + 1] - e0;
-                if (MODE == 1) {
-                    if (REG) cn_ms_reg<real, DMAX>(msg + e0, P.norm);
+                if constexpr (MODE == 1) {
+                    if constexpr (REG != 0) cn_ms_reg<real, DMAX>(msg + e0, P.norm);
                     else cn_ms<real>(msg + e0, d, P.norm);
                 } else {
-                    if (sizeof(real) == 8) cn_bp_exact<DMAX>((double*)(msg + e0), d);
+                    if constexpr (DMAX == 0) cn_bp_loop(msg + e0, d);                     // checks wider than 32 edges
+                    else if constexpr (sizeof(real) == 8) cn_bp_exact<DMAX>((double*)(msg + e0), d);
                     else cn_bp_f32<DMAX, (REG != 0 && DMAX % 2 == 0)>((float*)(msg + e0), d);
                 }
             }

@@ -8,6 +8,7 @@
 #include "pcl_common.cuh"
 #include "polar_scl.cuh"
 #include "polar_scl_fast.cuh"
+#include "polar_scl_wide.cuh"
 #include "polar_sc.cuh"
 #include "framegen.cuh"
 #include "ldpc_banked.cuh"
@@ -125,6 +126,7 @@ struct pcl_polar {
     int wpb, grid_max, smem_bytes;
     int last_grid = 0;
     int fast = 0;               // register-resident tree bottom (polar_scl_fast.cuh)
+    int wide = 0;               // list size above 32: one block per frame, a thread per slot (polar_scl_wide.cuh)
     int fpw = 1;                // fast kernel: frames per warp
     int NL = 0, GL = 0;         // fast kernel: compiled-in log2 N and G (0: run-time values)
     int TM = 0;                 // fast kernel, TM variant: one block per SM, mid levels in tensor / shared memory
@@ -220,6 +222,9 @@ static bool polar_fast_variant_exists(int LP, int nl, int gl, int tm = 0)
 template <typename real, typename Fn>
 static int polar_with_kernel(pcl_polar* h, Fn&& fn)
 {
+#ifndef PCL_QUICK
+    if (h->wide) return fn(polar_scl_wide_kernel<real>);
+#endif
     if (h->fast) {
 #define X(lp, n_, g_, tm_)                                                                     \
     if constexpr (n_ == 0 || sizeof(real) == 4) {                                                   \
@@ -292,7 +297,7 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
     if (N <= 0 || (N & (N - 1)) != 0) return fail(PCL_EINVAL, "N must be a power of 2");
     if (!(K > 0 && K < N)) return fail(PCL_EINVAL, "K must be in (0, N)");
     if (list_size < 1) return fail(PCL_EINVAL, "list_size must be >= 1");
-    if (list_size > 32) return fail(PCL_EUNSUPPORTED, "list_size %d > 32 is not supported by the one-warp-per-frame kernel", list_size);
+    if (list_size > 1024) return fail(PCL_EUNSUPPORTED, "list_size %d > 1024 is not supported (one thread per list slot, one block per frame)", list_size);
     if (N > 8192) return fail(PCL_EUNSUPPORTED, "N %d > 8192 is not supported", N);
     if (dtype != PCL_F32 && dtype != PCL_F64) return fail(PCL_EINVAL, "bad dtype");
     if (crc_len < 0 || crc_len > 32) return fail(PCL_EINVAL, "bad crc_len");
@@ -336,7 +341,29 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
                         n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 0) != 0);
     int bps = 1;
     bool placed = false;
-    for (int attempt = can_tm ? 0 : (can_fast ? 1 : 2); attempt < 3 && !placed; attempt++) {
+    if (LP > 32) {
+        // list wider than a warp: one block of LP threads per frame, every level in the global scratch
+        h->wide = 1; h->fast = 0; h->TM = 0; h->fpw = 1; h->NL = 0; h->GL = 0;
+        h->wpb = LP / 32;
+        PolarLayout& Y = h->lay;
+        Y = PolarLayout();
+        Y.N = N; Y.n = n; Y.K = K; Y.L = list_size; Y.G = n - 1;
+        Y.NW = N >= 32 ? N / 32 : 1;
+        Y.nb = n > 5 ? n - 5 : 0;
+        Y.uw_slots = LP;
+        h->smem_bytes = pcl_wide_smem_bytes(LP, n, Y.nb);
+        Y.warp_bytes = h->smem_bytes / h->wpb;
+        Y.scratch_per_warp = pcl_wide_scratch_bytes(LP, N, rsz) / rsz / h->wpb;
+        if (h->smem_bytes <= di.smem_per_block) {
+#ifndef PCL_EMU
+            rc = (dtype == PCL_F64) ? polar_occ<double>(h, h->wpb * 32, h->smem_bytes, &bps)
+                                    : polar_occ<float>(h, h->wpb * 32, h->smem_bytes, &bps);
+            if (rc) { delete h; return rc; }
+#endif
+            placed = bps >= 1;
+        }
+    }
+    for (int attempt = can_tm ? 0 : (can_fast ? 1 : 2); attempt < 3 && !placed && !h->wide; attempt++) {
         h->TM = attempt == 0;
         h->fast = attempt <= 1;
         if (attempt == 1 && !can_fast) continue;
@@ -400,6 +427,12 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
     }
     h->grid_max = di.sms * bps;
     h->scratch_bytes = (size_t)h->grid_max * h->wpb * h->lay.scratch_per_warp * rsz;
+    if (h->wide) {
+        const int64_t per_block = pcl_wide_scratch_bytes(LP, N, rsz);
+        const int64_t cap = std::max<int64_t>(1, ((int64_t)4 << 30) / per_block);       // at most 4 GiB of scratch
+        h->grid_max = (int)std::min<int64_t>(h->grid_max, cap);
+        h->scratch_bytes = (size_t)h->grid_max * (size_t)per_block;
+    }
 
     if (cudaMalloc((void**)&h->d_frozen_words, NW * 4) != cudaSuccess ||
         cudaMalloc((void**)&h->d_info_pos, (size_t)K * 2) != cudaSuccess) {
@@ -451,7 +484,7 @@ extern "C" int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block
                                      int* fast)
 {
     if (!h) return fail(PCL_EINVAL, "null handle");
-    if (fast) *fast = h->sc256 ? 4 : (h->fast ? (h->TM ? 3 : (h->NL ? 2 : 1)) : 0);
+    if (fast) *fast = h->wide ? 5 : (h->sc256 ? 4 : (h->fast ? (h->TM ? 3 : (h->NL ? 2 : 1)) : 0));
     if (grid) *grid = h->last_grid;
     if (block) *block = h->wpb * 32;
     if (smem_bytes) *smem_bytes = h->smem_bytes;
@@ -543,7 +576,9 @@ static int polar_decode_impl(pcl_polar* h, const void* llr_dev, int64_t F, uint8
     P.use_crc = h->crc_len > 0;
     P.crc_len = h->crc_len;
     P.crc_poly = h->crc_poly;
-    const int64_t fpb = (int64_t)h->wpb * h->fpw;            // frames per block per pass
+    if (h->wide && leaf_dev != nullptr && h->LP > 256)
+        return fail(PCL_EUNSUPPORTED, "per-leaf dumps carry the parent slot in one byte: list size %d > 256", h->L);
+    const int64_t fpb = h->wide ? 1 : (int64_t)h->wpb * h->fpw;            // frames per block per pass
     int64_t need = (F + fpb - 1) / fpb;
     int grid = (int)std::min<int64_t>(need, h->grid_max);
     P.next = nullptr;
@@ -597,7 +632,7 @@ extern "C" int pcl_polar_decode_host_ex(pcl_polar_t* h, const void* llr_host, in
         }
     }
     // a chunk fills the resident grid at least once and carries >= 32 MiB of LLRs
-    const int64_t resident = (int64_t)h->grid_max * h->wpb * h->fpw;
+    const int64_t resident = h->wide ? (int64_t)h->grid_max : (int64_t)h->grid_max * h->wpb * h->fpw;
     int64_t chunk = std::max<int64_t>(resident, ((int64_t)32 << 20) / ((int64_t)h->N * 4));
     chunk = (chunk + 255) / 256 * 256;
     chunk = env_int("PCL_HOST_CHUNK", (int)std::min<int64_t>(chunk, 1 << 20));
@@ -664,7 +699,8 @@ static int ldpc_with_kernel_c(pcl_ldpc* h, Fn&& fn)
 #endif
     if (h->dmax <= 8) return fn(ldpc_decode_kernel<real, 0, 8, 0, COOP>);
     if (h->dmax <= 16) return fn(ldpc_decode_kernel<real, 0, 16, 0, COOP>);
-    return fn(ldpc_decode_kernel<real, 0, 32, 0, COOP>);
+    if (h->dmax <= 32) return fn(ldpc_decode_kernel<real, 0, 32, 0, COOP>);
+    return fn(ldpc_decode_kernel<real, 0, 0, 0, COOP>);           // any check degree (cn_bp_loop)
 }
 
 template <typename real, typename Fn>
@@ -741,7 +777,6 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
             return fail(PCL_EDEGREE1, "zero-size array to reduction operation minimum which has no identity");
     }
     for (int v = 0; v < n; v++) vmax = std::max(vmax, vdeg[v]);
-    if (mode == PCL_LDPC_BP && dmax > 32) return fail(PCL_EUNSUPPORTED, "check degree %d > 32 not supported", dmax);
     if (vmax > 128) return fail(PCL_EUNSUPPORTED, "variable degree %d > 128 not supported", vmax);
 
     pcl_ldpc* h = new pcl_ldpc();

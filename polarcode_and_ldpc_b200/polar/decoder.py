@@ -12,7 +12,9 @@ Differences, all additive:
     stores the flag but never applies it (decoder.py:202-203, 259), so this rule
     has no reference behaviour to match ("parity unpinned"); with use_crc=False
     the result is the reference's.
-  * list_size is limited to 32 and N to 8192 (NotImplementedError beyond).
+  * list sizes up to 32 run one path per lane (a warp carries 32 / L frames); 33 .. 1024 run one
+    block per frame with a thread per slot (polar_scl_wide.cuh); N is limited to 8192 and list_size
+    to 1024 (NotImplementedError beyond; per-leaf dumps stop at list size 256).
 There is no CPU path: constructing a decoder without a CUDA device raises.
 """
 from __future__ import annotations
@@ -117,6 +119,10 @@ class _PolarBase:
         if fa.value == 4:
             return {"grid": g.value, "block": 96, "smem_bytes": 3 * 32 * 260 * 4, "global_levels": 0, "kernel": "polar_sc256_kernel",
                     "lanes_per_path": 1, "frames_per_warp": 32, "compiled_code_length": True, "tensor_memory": False}
+        if fa.value == 5:
+            return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "global_levels": lv.value,
+                    "kernel": "polar_scl_wide_kernel", "lanes_per_path": 1, "frames_per_block": 1,
+                    "compiled_code_length": False, "tensor_memory": False}
         return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "global_levels": lv.value,
                 "kernel": "polar_scl_fast_kernel" if fa.value else "polar_scl_kernel",
                 "lanes_per_path": 1 if fa.value else 32 // self._LP,

@@ -15,6 +15,8 @@ Fixtures
   polar_scl.npz  SCLDecoder (src/polar/decoder.py:176)  bits, path_metrics, leaf LLRs
   ldpc.npz       BPDecoder / MSDecoder (src/ldpc/decoder.py:11,208) bits, iterations, totals
   doc_kat.npz    docs/SCL_DECODER_README.md:115-128 flow (tests/test_scl_decoder.py:13-48)
+  wide.npz       what the reference accepts beyond a warp's width: SCLDecoder with list_size > 32
+                 (decoder.py:194-196) and a BP check of degree > 32 (`python gen_golden.py wide`)
 """
 import importlib.util
 import os
@@ -230,7 +232,64 @@ def gen_doc_kat():
     print("doc KAT:", message, codeword, llr[:3])
 
 
+def gen_wide():
+    rng = np.random.default_rng(31337)
+    np.random.seed(9001)
+    out = {}
+    scl_cases = [  # N, K, L, frozen kind, F, snr, kind
+        (64, 32, 64, "random", 3, 0.0, "awgn"), (128, 64, 40, "bhatt", 2, -1.0, "awgn"),
+        (32, 16, 48, "random", 3, 0.0, "int"), (64, 40, 100, "random", 2, 1.0, "raw"),
+    ]
+    for ci, (N, K, L, fk, F, snr, kind) in enumerate(scl_cases):
+        frozen = np.sort(rng.choice(N, N - K, replace=False)) if fk == "random" else \
+            pconstr.bhattacharyya_frozen_set(N, K, 2.0)
+        llr = polar_inputs(rng, N, K, frozen, F, snr, kind)
+        dec = SCLDecoder(N, K, list_size=L, frozen_bits=frozen)
+        bits, pm = [], []
+        for f in range(F):
+            bits.append(dec.decode(llr[f]))
+            pm.append(dec.path_metrics.copy())
+        out[f"scl{ci}_N"] = N
+        out[f"scl{ci}_L"] = L
+        out[f"scl{ci}_frozen"] = np.asarray(frozen, dtype=np.int64)
+        out[f"scl{ci}_llr"] = llr
+        out[f"scl{ci}_bits"] = np.array(bits, dtype=np.int64)
+        out[f"scl{ci}_pm"] = np.array(pm)
+        print("wide scl case", ci, N, K, L, "done", flush=True)
+    out["nscl"] = len(scl_cases)
+    # parity checks of degree 44 and 70 next to ordinary ones, a degree-1 check
+    r = np.random.RandomState(11)
+    m, n = 12, 90
+    H = np.zeros((m, n), dtype=int)
+    for c in range(m):
+        H[c, r.choice(n, r.randint(3, 9), replace=False)] = 1
+    H[2, r.choice(n, 40, replace=False)] = 1
+    H[5, :] = 0
+    H[5, r.choice(n, 70, replace=False)] = 1
+    H[9, :] = 0
+    H[9, 7] = 1
+    llr = rng.normal(1.5, 2.0, size=(5, n))
+    for name, es in (("dense_bp", True), ("dense_bp_nostop", False)):
+        dec = _BPTotals(H, max_iter=6, early_stop=es)
+        bits, iters, tots = [], [], []
+        for f in range(llr.shape[0]):
+            b, k = dec.decode(llr[f], return_iterations=True)
+            bits.append(b); iters.append(k); tots.append(dec._last_totals.copy())
+        out[name + "_H"] = H.astype(np.uint8)
+        out[name + "_cfg"] = np.array([0, 6, int(es)], dtype=np.int64)
+        out[name + "_llr"] = llr
+        out[name + "_bits"] = np.array(bits, dtype=np.int64)
+        out[name + "_iters"] = np.array(iters, dtype=np.int64)
+        out[name + "_total"] = np.array(tots)
+        print("wide ldpc case", name, "degrees", H.sum(1), "iters", iters, flush=True)
+    np.savez_compressed(os.path.join(HERE, "wide.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":
+        gen_wide()
+        sys.exit(0)
     gen_doc_kat()
     gen_ldpc()
     gen_polar()
+    gen_wide()

@@ -387,7 +387,7 @@ def test_edge_cases_and_errors():
     with pytest.raises(AssertionError):
         P.SCLDecoder(64, 64)
     with pytest.raises(NotImplementedError):
-        P.SCLDecoder(64, 32, list_size=64)
+        P.SCLDecoder(64, 32, list_size=2048)       # one thread per slot: a block holds at most 1024
     assert dec.L == 4 and dec.K == 32 and dec.n == 6 and len(dec.info_bits) == 32
     # default frozen set rule (reference: polar/utils.py:64-75)
     d2 = P.SCDecoder(16, 8)
@@ -588,3 +588,61 @@ def test_large_codes():
     assert np.array_equal(b, rb) and np.array_equal(it, ri)
     b, it = P.BPDecoder(H, max_iter=20).decode_batch(llr, return_iterations=True)
     assert int(((b != rb).any(axis=1) | (it != ri)).sum()) == 0
+
+
+# ------------------------------------------------- beyond a warp's width ------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_wide_list_and_wide_checks_golden(golden_dir, dtype):
+    """list_size 40 .. 100 (polar_scl_wide_kernel: a block per frame, a thread per slot) and BP checks
+    of degree 44 / 70 (cn_bp_loop) against vectors the reference produced (tests/golden/wide.npz)."""
+    g = _g(golden_dir, "wide.npz")
+    for ci in range(int(g["nscl"])):
+        N, L, fz, llr = int(g[f"scl{ci}_N"]), int(g[f"scl{ci}_L"]), g[f"scl{ci}_frozen"], g[f"scl{ci}_llr"]
+        dec = P.SCLDecoder(N, N - len(fz), list_size=L, frozen_bits=fz, dtype=dtype)
+        assert dec.launch_info()["kernel"] == "polar_scl_wide_kernel"
+        bits, pm = dec.decode_batch(llr, return_path_metrics=True)
+        ref = g[f"scl{ci}_pm"]
+        if dtype == "float32" and np.all(llr == np.round(llr)):
+            np.testing.assert_allclose(pm.max(axis=1), ref.max(axis=1), rtol=1e-5, atol=1e-5)   # integer-LLR ties, see test_scl_golden
+            continue
+        assert np.array_equal(bits, g[f"scl{ci}_bits"]), f"wide SCL case {ci} {dtype}"
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(pm), fin)
+        if dtype == "float64":
+            np.testing.assert_allclose(pm[fin], ref[fin], rtol=1e-12, atol=1e-11)
+        else:
+            assert _rel_err(pm[fin], ref[fin], float(np.mean(np.abs(llr)))) < 1e-4
+        assert np.array_equal(dec.decode(llr[0]), bits[0])
+    for name in ("dense_bp", "dense_bp_nostop"):
+        _, it, es = (int(x) for x in g[name + "_cfg"])
+        H, llr = g[name + "_H"].astype(np.int64), g[name + "_llr"]
+        dec = P.BPDecoder(H, max_iter=it, early_stop=bool(es), dtype=dtype)
+        bits, iters, tot = dec.decode_batch(llr, return_iterations=True, return_total_llr=True)
+        assert np.array_equal(bits, g[name + "_bits"]) and np.array_equal(iters, g[name + "_iters"]), name
+        if dtype == "float64":
+            np.testing.assert_allclose(tot, g[name + "_total"], rtol=1e-9, atol=1e-9)
+        else:
+            assert _rel_err(tot, g[name + "_total"], float(np.mean(np.abs(llr)))) < 1e-4
+
+
+def test_wide_list_bulk_parity():
+    """SCL-64 and SCL-128 at N = 1024 / 256 against the oracle: fp64 identical, fp32 pooled >= 99.99 %;
+    a wider list never decodes worse than a narrower one on the same frames (property at full size)."""
+    rng = np.random.default_rng(64)
+    tot = bad = 0
+    for N, K, L, F, snr in ((1024, 512, 64, 192, 0.0), (256, 128, 128, 256, -1.0), (512, 256, 33, 256, 0.0)):
+        fz = P.bhattacharyya_frozen_set(N, K, 2.0)
+        enc = P.PolarEncoder(N, K, fz)
+        msg = rng.integers(0, 2, size=(F, K))
+        np.random.seed(N + L)
+        llr = P.AWGNChannel(snr).transmit_batch(enc.encode_batch(msg))
+        ref = oracle.polar_scl(N, L, fz, llr, nthreads=oracle.max_threads())
+        got64 = P.SCLDecoder(N, K, list_size=L, frozen_bits=fz, dtype="float64").decode_batch(llr)
+        assert np.array_equal(got64, ref), f"fp64 wide list N={N} L={L}"
+        got32 = P.SCLDecoder(N, K, list_size=L, frozen_bits=fz, dtype="float32").decode_batch(llr)
+        bad += int((got32 != ref).any(axis=1).sum())
+        tot += F
+        fer_wide = (ref != msg).any(axis=1).mean()
+        fer_8 = (P.SCLDecoder(N, K, list_size=8, frozen_bits=fz).decode_batch(llr) != msg).any(axis=1).mean()
+        assert fer_wide <= fer_8 + 0.02
+    assert bad == 0, f"{bad} of {tot} fp32 frames differ"

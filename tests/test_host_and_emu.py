@@ -177,6 +177,41 @@ def test_emu_polar_large_code_falls_back_instead_of_failing():
     assert np.array_equal(emu.polar_decode(N, K, 2, fz, llr, "f32", crc=(0x1D, 8)), ref)
 
 
+def test_emu_wide_list_and_wide_checks(golden_dir):
+    """Beyond a warp's width: list sizes 40 .. 100 through the block-per-frame
+    kernel (polar_scl_wide.cuh), both lane orders, CRC selection, and BP checks of degree 44 / 70 through
+    the any-degree rule (cn_bp_loop) -- against vectors the reference itself produced."""
+    g = np.load(os.path.join(golden_dir, "wide.npz"))
+    for ci in range(int(g["nscl"])):
+        N, L, fz, llr = int(g[f"scl{ci}_N"]), int(g[f"scl{ci}_L"]), g[f"scl{ci}_frozen"], g[f"scl{ci}_llr"]
+        for reverse in (False, True):
+            bits, pm = emu.polar_decode(N, N - len(fz), L, fz, llr, "f64", want_pm=True, reverse=reverse)[:2]
+            assert np.array_equal(bits, g[f"scl{ci}_bits"]), f"wide case {ci}"
+            ref = g[f"scl{ci}_pm"]
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(pm), fin)
+            np.testing.assert_allclose(pm[fin], ref[fin], rtol=1e-12, atol=1e-11)
+    N, K, L = 128, 70, 64
+    fz = P.bhattacharyya_frozen_set(N, K, 2.0)
+    enc = P.PolarEncoder(N, K, fz, use_crc=True)
+    rng = np.random.default_rng(12)
+    np.random.seed(12)
+    llr = P.AWGNChannel(0.0).transmit_batch(enc.encode_batch(rng.integers(0, 2, size=(3, enc.K_data))))
+    for dt in ("f64", "f32"):
+        assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, dt), oracle.polar_scl(N, L, fz, llr))
+        assert np.array_equal(emu.polar_decode(N, K, L, fz, llr, dt, crc=(0x1D, 8)),
+                              oracle.polar_scl(N, L, fz, llr, use_crc=True))
+    for name in ("dense_bp", "dense_bp_nostop"):
+        _, it, es = (int(x) for x in g[name + "_cfg"])
+        H = g[name + "_H"].astype(np.int64)
+        bits, iters, tot = emu.ldpc_decode(H, g[name + "_llr"], "bp", it, 1.0, bool(es), "f64", want_total=True)
+        assert np.array_equal(bits, g[name + "_bits"]) and np.array_equal(iters, g[name + "_iters"])
+        np.testing.assert_allclose(tot, g[name + "_total"], rtol=1e-9, atol=1e-9)
+        bits, iters, tot = emu.ldpc_decode(H, g[name + "_llr"], "bp", it, 1.0, bool(es), "f32", want_total=True)
+        assert np.array_equal(bits, g[name + "_bits"]) and np.array_equal(iters, g[name + "_iters"])
+        assert np.max(np.abs(tot - g[name + "_total"]) / np.maximum(np.abs(g[name + "_total"]), 1.0)) < 1e-4
+
+
 def test_emu_ldpc_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "ldpc.npz"))
     for name in g["names"]:

@@ -87,3 +87,24 @@ def test_threads_same_result(golden_dir):
     a = oracle.polar_scl(N, L, g[f"c{ci}_frozen"], g[f"c{ci}_llr"], nthreads=1)
     b = oracle.polar_scl(N, L, g[f"c{ci}_frozen"], g[f"c{ci}_llr"], nthreads=4)
     assert np.array_equal(a, b)
+
+
+def test_wide_golden(golden_dir):
+    """List sizes above 32 and a BP check of degree 44 / 70: what the reference accepts beyond the
+    width of a warp (tests/golden/gen_golden.py::gen_wide ran the reference)."""
+    g = _load(golden_dir, "wide.npz")
+    for ci in range(int(g["nscl"])):
+        N, L = int(g[f"scl{ci}_N"]), int(g[f"scl{ci}_L"])
+        bits, pm = oracle.polar_scl(N, L, g[f"scl{ci}_frozen"], g[f"scl{ci}_llr"], want_pm=True)
+        assert np.array_equal(bits, g[f"scl{ci}_bits"]), f"wide SCL case {ci}"
+        ref = g[f"scl{ci}_pm"]
+        assert np.array_equal(np.isinf(pm), np.isinf(ref))
+        fin = np.isfinite(ref)
+        np.testing.assert_allclose(pm[fin], ref[fin], rtol=1e-12, atol=1e-12)
+    for name in ("dense_bp", "dense_bp_nostop"):
+        _, it, es = (int(x) for x in g[name + "_cfg"])
+        bits, iters, total = oracle.ldpc(g[name + "_H"].astype(np.int64), g[name + "_llr"], mode="bp", max_iter=it,
+                                         early_stop=bool(es), want_total=True)
+        assert np.array_equal(bits, g[name + "_bits"]), name
+        assert np.array_equal(iters, g[name + "_iters"]), name
+        np.testing.assert_allclose(total, g[name + "_total"], rtol=1e-9, atol=1e-9, err_msg=name)
