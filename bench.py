@@ -80,7 +80,8 @@ def algorithmic_bytes(w):
         N, K, L = w["N"], w["K"], w["L"]
         return L * N * int(np.log2(N)) * 12 + 4 * N + K
     n, E = w["n"], 3 * w["n"]
-    return w["iters"] * (16 * E + 4 * n) + 5 * n
+    # with the syndrome early stop the figure scales with the MEAN iteration count of the batch
+    return w.get("mean_iters", w["iters"]) * (16 * E + 4 * n) + 5 * n
 
 
 def io_bytes(w):
@@ -371,6 +372,10 @@ def run_gpu_workload(name, steps, warmup, env, snr=None, frames=None, with_e2e=F
     }
     if world > 1:
         res["per_rank_ms_kernel"] = [float(x) for x in per_rank[:, 1]]
+    if w["kind"] == "ldpc" and w.get("early_stop"):
+        _, its = dec.decode_batch(llr[: min(F, 65536)], return_iterations=True)       # outside the timed region
+        w["mean_iters"] = float(its.float().mean().item())
+        res["mean_iterations"] = w["mean_iters"]
     res["roofline"] = roofline(name, w, med_kern, F, res["launch"])
 
     # ---- end to end through the C-ABI host-buffer call --------------------------
@@ -454,9 +459,12 @@ def roofline(name, w, ms_kernel, F, launch):
                     "traffic_bytes_per_frame": traffic_pf, "traffic_source": traffic_src,
                     "traffic_over_io": (traffic_pf / io) if traffic_pf is not None else None}}
     if w["kind"] == "ldpc" and w["mode"] == "bp":
-        ops = 3 * 3 * w["n"] * w["iters"]                  # 3 MUFU per edge per iteration (ex2; rcp, lg2)
+        # MUFU per edge per iteration: ex2 in, lg2 out, and a reciprocal per edge (3) or per PAIR of edges (2.5:
+        # the banked kernel decodes two checks per lane and shares the reciprocal, ldpc_bp.cuh cn_bp_core2)
+        per_edge = 2.5 if launch.get("kernel") == "ldpc_banked_kernel" else 3.0
+        ops = per_edge * 3 * w["n"] * w.get("mean_iters", w["iters"])
         g = ops * F / (ms_kernel * 1e-3) / 1e9
-        r["mufu"] = {"ops_per_frame": ops, "achieved_gops": g, "peak": pk["mufu_gops"], "peak_source": pk["mufu_source"],
+        r["mufu"] = {"ops_per_frame": ops, "mufu_per_edge": per_edge, "achieved_gops": g, "peak": pk["mufu_gops"], "peak_source": pk["mufu_source"],
                      "frac": g / pk["mufu_gops"]}
     return r
 

@@ -248,6 +248,12 @@ static int polar_with_kernel(pcl_polar* h, Fn&& fn)
     return fail(PCL_EUNSUPPORTED, "no kernel for list size %d", h->L);
 }
 
+template <typename Fn>
+static int polar_with_kernel_dtype(pcl_polar* h, Fn&& fn)
+{
+    return h->dtype == PCL_F64 ? polar_with_kernel<double>(h, fn) : polar_with_kernel<float>(h, fn);
+}
+
 template <typename real>
 static int polar_launch(pcl_polar* h, const PolarParams<real>& P, int grid, void* stream)
 {
@@ -264,6 +270,10 @@ static int polar_occ(pcl_polar* h, int threads, int smem, int* bps)
 {
     return polar_with_kernel<real>(h, [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // the occupancy query honours the function's CURRENT carve-out preference: ask with the largest
+        // shared-memory split, not with whatever an earlier handle of the same kernel left behind (seen: 4
+        // instead of 6 resident blocks for a handle created after one with a bigger block)
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem));
         // Ask for the shared-memory carve-out the computed residency needs.  Left to its default the
         // driver may keep the split of the kernel that ran before (seen after the polar kernel: half
@@ -338,7 +348,7 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
     const bool can_fast = n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 && env_int("PCL_POLAR_GENERIC", 0) == 0;
     const bool nl_ok = compiled_ok && env_int("PCL_POLAR_NL", 1) != 0;
     const bool can_tm = can_fast && dtype == PCL_F32 && nl_ok && env_int("PCL_POLAR_TM", 1) != 0 &&
-                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 0) != 0);
+                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 1) != 0);
     int bps = 1;
     bool placed = false;
     if (LP > 32) {
@@ -422,8 +432,30 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
                     need, di.smem_per_block);
     }
     {
-        const int cap = env_int("PCL_POLAR_BPS", 0);     // experiment knob: resident blocks per SM
-        if (cap > 0 && cap < bps) bps = cap;
+        int cap = env_int("PCL_POLAR_BPS", 0);           // experiment knob: resident blocks per SM
+        // Small lists outside the tensor-memory variant keep most tree levels in the global scratch and re-read
+        // the lower ones constantly: leave >= 60 KB of the SM's 228 KB to L1 instead of filling it with blocks
+        // (scripts/sweep_resident_blocks.py: SC N=1024 28.5 -> 41.9 Gbps at 5 instead of 6 blocks, N=2048
+        // 23.7 -> 30.2, SCL-4 13.5 -> 16.1, SCL-8 N=2048 6.0 -> 7.05; lists of 16 and 32 prefer the blocks).
+        if (cap <= 0 && h->fast && !h->TM && !h->wide && LP <= 8) {
+            const int l1kb = env_int("PCL_POLAR_L1KB", 60);
+            if (l1kb > 0) cap = std::max(1, (di.smem_per_sm - l1kb * 1024) / (h->smem_bytes + 1024));
+        }
+        if (cap > 0 && cap < bps) {
+            bps = cap;
+#ifndef PCL_EMU
+            // fewer resident blocks: give the shared memory they do not use back to L1 (the level scratch is
+            // read through it)
+            const int smem_need = h->smem_bytes;
+            rc = polar_with_kernel_dtype(h, [&](auto kern) -> int {
+                long need = (long)bps * (smem_need + 1024);
+                int pct = (int)((need * 100 + di.smem_per_sm - 1) / di.smem_per_sm);
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+                return PCL_OK;
+            });
+            if (rc) { delete h; return rc; }
+#endif
+        }
     }
     h->grid_max = di.sms * bps;
     h->scratch_bytes = (size_t)h->grid_max * h->wpb * h->lay.scratch_per_warp * rsz;
@@ -726,6 +758,10 @@ static int ldpc_occ(pcl_ldpc* h, int threads, int smem, int* bps)
 {
     return ldpc_with_kernel<real>(h, [&](auto kern) -> int {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // the occupancy query honours the function's CURRENT carve-out preference: ask with the largest
+        // shared-memory split, not with whatever an earlier handle of the same kernel left behind (seen: 4
+        // instead of 6 resident blocks for a handle created after one with a bigger block)
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem));
         // Ask for the shared-memory carve-out the computed residency needs.  Left to its default the
         // driver may keep the split of the kernel that ran before (seen after the polar kernel: half

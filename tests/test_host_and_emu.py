@@ -159,6 +159,12 @@ def test_emu_polar_tensor_memory_variant():
         assert np.array_equal(got, ref)
     got = emu.polar_decode(N, K, L, fz, llr[:9], "f32", env={"PCL_POLAR_TM": 0})
     assert emu.polar_decode.last_fast == 2 and np.array_equal(got, ref[:9])
+    # list size 32 takes the same variant by default (one frame per warp)
+    ref32 = oracle.polar_scl(N, 32, fz, llr[:5])
+    got = emu.polar_decode(N, K, 32, fz, llr[:5], "f32")
+    assert emu.polar_decode.last_fast == 3 and np.array_equal(got, ref32)
+    got = emu.polar_decode(N, K, 32, fz, llr[:5], "f32", env={"PCL_POLAR_TM32": 0})
+    assert emu.polar_decode.last_fast == 2 and np.array_equal(got, ref32)
 
 
 def test_emu_polar_large_code_falls_back_instead_of_failing():
