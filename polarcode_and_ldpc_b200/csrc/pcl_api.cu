@@ -204,7 +204,7 @@ static void polar_layout(PolarLayout& Y, int N, int K, int L, int LP, int G, int
 #define PCL_POLAR_FAST_VARIANTS(X) \
     X(1, 0, 0, 0) X(2, 0, 0, 0) X(4, 0, 0, 0) X(8, 0, 0, 0) X(16, 0, 0, 0) X(32, 0, 0, 0) \
     X(8, 7, 1, 0) X(8, 8, 2, 0) X(8, 9, 4, 0) X(8, 10, 5, 0) X(8, 11, 7, 0) X(8, 12, 8, 0) X(32, 10, 5, 0) X(1, 8, 2, 0) \
-    X(8, 10, 3, 1) X(32, 10, 3, 1)
+    X(8, 10, 3, 1) X(16, 10, 3, 1) X(32, 10, 3, 1) X(8, 11, 4, 1) X(8, 12, 5, 1)
 #endif
 // (SCL-8 gains 1.2-1.9 x from a compiled code length at every N = 128 .. 4096.  SC, LP = 1, does
 // not in general -- N = 1024: 29 Gbps compiled vs 40 at run time; with no prune its time is all
@@ -348,7 +348,7 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
     const bool can_fast = n >= 4 && (n - 4) * pb <= 32 && (n > 5 ? n - 5 : 0) * pb <= 32 && env_int("PCL_POLAR_GENERIC", 0) == 0;
     const bool nl_ok = compiled_ok && env_int("PCL_POLAR_NL", 1) != 0;
     const bool can_tm = can_fast && dtype == PCL_F32 && nl_ok && env_int("PCL_POLAR_TM", 1) != 0 &&
-                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 1) != 0);
+                        n >= 9 && polar_fast_variant_exists(LP, n, n - 7, 1) && (LP == 8 || env_int("PCL_POLAR_TM32", 1) != 0)   /* PCL_POLAR_TM32=0: lists of 16 / 32 back on the round-1 layout */;
     int bps = 1;
     bool placed = false;
     if (LP > 32) {
