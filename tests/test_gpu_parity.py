@@ -174,6 +174,29 @@ def test_scl8_kernel_variants_agree():
     assert np.array_equal(outs["tm"], outs["nl"]) and np.array_equal(outs["tm"], outs["rt"])
 
 
+@pytest.mark.parametrize("N,K,L,F", [(1024, 512, 16, 6000), (1024, 686, 32, 3000), (2048, 1024, 8, 6000), (4096, 2048, 8, 3000)])
+def test_tensor_memory_variants_other_sizes(N, K, L, F):
+    """The tensor-memory variant is also compiled for list sizes 16 / 32 at N = 1024 and for SCL-8 at
+    N = 2048 / 4096: same bits as the round-1 layout (PCL_POLAR_TM=0) on every frame, and the oracle's bits
+    on a subset (fp32 pooled gate in test_compiled_code_length_variants / the headline test)."""
+    frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+    _, llr = _polar_frames(N, K, frozen, F, 0.0, N + L)
+    dev = torch.from_numpy(llr).cuda().float()
+    dec = P.SCLDecoder(N, K, list_size=L, frozen_bits=frozen)
+    assert dec.launch_info()["tensor_memory"]
+    tm = dec.decode_batch(dev).cpu().numpy()
+    os.environ["PCL_POLAR_TM"] = "0"
+    try:
+        dec0 = P.SCLDecoder(N, K, list_size=L, frozen_bits=frozen)
+        assert not dec0.launch_info()["tensor_memory"]
+        assert np.array_equal(tm, dec0.decode_batch(dev).cpu().numpy())
+    finally:
+        os.environ.pop("PCL_POLAR_TM")
+    sub = min(F, 512)
+    ref = oracle.polar_scl(N, L, frozen, llr[:sub], nthreads=oracle.max_threads())
+    assert int((tm[:sub] != ref).any(axis=1).sum()) == 0
+
+
 def test_scl32_rates_parity():
     """BASELINE config 4: SCL L=32 N=1024 at rates .50/.67/.75/.83."""
     N, L = 1024, 32

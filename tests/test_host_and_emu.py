@@ -165,6 +165,14 @@ def test_emu_polar_tensor_memory_variant():
     assert emu.polar_decode.last_fast == 3 and np.array_equal(got, ref32)
     got = emu.polar_decode(N, K, 32, fz, llr[:5], "f32", env={"PCL_POLAR_TM32": 0})
     assert emu.polar_decode.last_fast == 2 and np.array_equal(got, ref32)
+    # ... and so do list size 16 and SCL-8 at N = 2048 (two levels in the global scratch instead of one)
+    got = emu.polar_decode(N, K, 16, fz, llr[:6], "f32", reverse=True)
+    assert emu.polar_decode.last_fast == 3 and np.array_equal(got, oracle.polar_scl(N, 16, fz, llr[:6]))
+    N2, K2 = 2048, 1024
+    fz2 = P.bhattacharyya_frozen_set(N2, K2, 2.0)
+    llr2 = P.AWGNChannel(-0.5).transmit_batch(P.PolarEncoder(N2, K2, fz2).encode_batch(rng.integers(0, 2, size=(9, K2))))
+    got = emu.polar_decode(N2, K2, 8, fz2, llr2, "f32")
+    assert emu.polar_decode.last_fast == 3 and np.array_equal(got, oracle.polar_scl(N2, 8, fz2, llr2))
 
 
 def test_emu_polar_large_code_falls_back_instead_of_failing():
