@@ -37,3 +37,17 @@ for n in (96,504):
     H=P.gallager_parity_check(n,3,6,42); G,_=P.generator_from_parity(H)
     emu.gen_frames('ldpc',n,G.shape[0],G,5,1.0,seed=4)
 print('asan run ok')
+# round 2: lists wider than a warp (block per frame), checks wider than 32 edges, tensor-memory variants of other sizes
+g=np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),'golden','wide.npz'))
+for ci in range(int(g['nscl'])):
+    N,L,fz,llr=int(g[f'scl{ci}_N']),int(g[f'scl{ci}_L']),g[f'scl{ci}_frozen'],g[f'scl{ci}_llr']
+    for dt in ('f32','f64'):
+        got=emu.polar_decode(N,N-len(fz),L,fz,llr,dt,want_pm=True,want_leaf=(L<=256))[0]
+        if dt=='f64': assert np.array_equal(got,g[f'scl{ci}_bits']),ci
+emu.polar_decode(128,70,64,P.bhattacharyya_frozen_set(128,70,2.0),rng.normal(1,3,size=(2,128)),'f32',crc=(0x1D,8))
+for dt in ('f32','f64'):
+    emu.ldpc_decode(g['dense_bp_H'].astype(np.int64),g['dense_bp_llr'],'bp',6,1.0,True,dt,want_total=True)
+for N,K,L,F in ((1024,512,16,3),(1024,512,32,2),(2048,1024,8,5)):
+    fz=P.bhattacharyya_frozen_set(N,K,2.0); llr=rng.normal(1,3,size=(F,N))
+    assert np.array_equal(emu.polar_decode(N,K,L,fz,llr,'f32'),oracle.polar_scl(N,L,fz,llr)),(N,L)
+print('asan round-2 cases ok')
