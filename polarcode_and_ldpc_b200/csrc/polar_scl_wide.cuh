@@ -87,19 +87,22 @@ __global__ void __launch_bounds__(1024) polar_scl_wide_kernel(PolarParams<real> 
                 for (int d = start; d <= n; d++) {
                     const int sz = N >> d;
                     const int bit = (i >> (n - d)) & 1;
-                    const real* src = nullptr;
+                    // source and destination are different levels of the scratch: the loads of the next elements
+                    // need not wait for the stores of the previous ones
+                    const real* __restrict__ src = nullptr;
                     int q = 0;
                     if (d > 1) {
                         q = PL[(d - 2) * LP + p];
                         src = gl + (int64_t)LP * (N - (N >> (d - 2)));
                     }
-                    real* dst = (d < n) ? gl + (int64_t)LP * (N - (N >> (d - 1))) : nullptr;
+                    real* __restrict__ dst = (d < n) ? gl + (int64_t)LP * (N - (N >> (d - 1))) : nullptr;
                     int qb = 0;
                     const uint32_t* bsrc = nullptr;
                     if (bit && d <= nb) {
                         qb = PBp[(d - 1) * LP + p];
                         bsrc = bw + (int64_t)LP * ((N >> 5) - (N >> (d + 4)));
                     }
+#pragma unroll 4
                     for (int k = 0; k < sz; k++) {
                         real a, b;
                         if (d == 1) {
