@@ -588,6 +588,9 @@ struct pcl_sc_node<real, 1> {
 #ifndef PCL_FROZEN_BLOCK
 #define PCL_FROZEN_BLOCK 1    // an all-frozen block of 8 leaves as straight-line code (no leaf loop)
 #endif
+#ifndef PCL_RAW_BLOCK_BITS
+#define PCL_RAW_BLOCK_BITS 1  // decisions of the current block as raw bits 24 .. 31 of `small` (one OR per leaf); 0: folded fields per leaf
+#endif
 #ifndef PCL_SC_BLOCK
 #define PCL_SC_BLOCK 1        // list size 1 without a metric: unrolled 8-leaf recursion instead of the leaf loop
 #endif
@@ -897,7 +900,13 @@ polar_scl_fast_kernel(PolarParams<real> P)
             // all borrowed source arrays have been read: order before later overwrites
             __syncwarp();
 
-            uint32_t c4hi = 0;                    // partial sums of leaves 4 .. 7 (size-4 field of the upper half)
+            // Partial sums of the block being decoded.  PCL_RAW_BLOCK_BITS: leaf j ORs its decision into bit 24 + j of
+            // `small` (bit 31 = leaf 7 = what the final u-word wants there) and the three places that need folded
+            // sums -- g at leaves 2 / 6, g at leaf 4, the block's own sums c8 at its end -- fold them there, once;
+            // a survivor inherits the raw bits with `small`.  (Before: the fields of sizes 1, 2, 4 at bits 30, 28, 24
+            // were re-folded after every leaf behind three tests of j, 14 instructions per leaf.)
+            uint32_t c4hi = 0;                    // folded fields only: partial sums of leaves 4 .. 7
+            uint32_t c8 = 0;                      // the block's 8 partial sums, folded upwards below
             if (PCL_FROZEN_BLOCK && !EXACT && LP > 1 && fz8 == 0xffu && (!DBG || P.dbg_leaf == nullptr)) {
                 // ---- all-frozen block (46 of the 128 blocks of the headline code): no decisions, every
                 // g is a plain sum, so the 8 leaf LLRs are one straight-line butterfly and the 8 penalties
@@ -923,35 +932,58 @@ polar_scl_fast_kernel(PolarParams<real> P)
                     pmn -= (double)pen;
                 }
                 pm = act ? pmn : pm;              // an inactive slot keeps DEAD whatever its registers hold
+#if PCL_RAW_BLOCK_BITS
+                small &= 0x00ffffffu;             // eight zero decisions
+#else
                 small &= ~(127u << 24);           // fields of sizes 4, 2, 1: all zero
                 ulast = 0;
+#endif
             } else if (PCL_SC_BLOCK && LP == 1 && !P.want_pm && (!DBG || P.dbg_leaf == nullptr)) {
                 // ---- SC, bits only: the block as an unrolled recursion (pcl_sc_node) -----------------
                 uint32_t u8 = 0;
-                const uint32_t c8 = pcl_sc_node<real, 8>::run(R3, fz8, u8);
+                c8 = pcl_sc_node<real, 8>::run(R3, fz8, u8);
+#if PCL_RAW_BLOCK_BITS
+                small = (small & 0x00ffffffu) | (u8 << 24);
+#else
                 c4hi = c8 >> 4;
                 // fields as the leaf loop leaves them: size 4 = sums of leaves 0 .. 3, size 2 = (u4 ^ u5, u5), size 1 = u6
                 small = (small & ~(127u << 24)) | (((c8 ^ (c8 >> 4)) & 15u) << 24) |
                         ((((u8 >> 4) ^ (u8 >> 5)) & 1u) << 28) | (((u8 >> 5) & 1u) << 29) | (((u8 >> 6) & 1u) << 30);
                 ulast = (u8 >> 7) & 1u;
+#endif
             } else {
             // ---- the 8 leaves of the block (rolled: the body must stay I-cache resident) ----
             real R2[4], R1[2];
 #pragma unroll
             for (int t = 0; t < 4; t++) R2[t] = (real)0;
             R1[0] = R1[1] = (real)0;
+#if PCL_RAW_BLOCK_BITS
+            small &= 0x00ffffffu;
+#endif
 #pragma unroll 1
             for (int j = 0; j < 8; j++) {
                 // heights to recompute: j == 0 -> 2,1,0; else ctz(j) .. 0; f or g per bit of j.
                 // small: size-4 field at bits 24..27, size-2 at 28..29, size-1 at 30
                 real x;
                 if (j & 1) {
+#if PCL_RAW_BLOCK_BITS
+                    x = pcl_fast<real>::gs(R1[0], R1[1], small << (8 - j));          // u[j-1] sits at bit 23 + j
+#else
                     x = pcl_fast<real>::gs(R1[0], R1[1], small << 1);
+#endif
                 } else {
                     if ((j & 2) == 0) {
                         if (j & 4) {
+#if PCL_RAW_BLOCK_BITS
+                            uint32_t c4 = small >> 24;                               // u0 .. u3 -> their partial sums
+                            c4 ^= (c4 >> 1) & 5u;
+                            c4 ^= (c4 >> 2) & 3u;
+#pragma unroll
+                            for (int t = 0; t < 4; t++) R2[t] = pcl_fast<real>::gs(R3[t], R3[t + 4], c4 << (31 - t));
+#else
 #pragma unroll
                             for (int t = 0; t < 4; t++) R2[t] = pcl_fast<real>::gs(R3[t], R3[t + 4], small << (7 - t));
+#endif
                         } else {
 #pragma unroll
                             for (int t = 0; t < 4; t++) R2[t] = pcl_math<real>::f(R3[t], R3[t + 4]);
@@ -959,8 +991,14 @@ polar_scl_fast_kernel(PolarParams<real> P)
                         R1[0] = pcl_math<real>::f(R2[0], R2[2]);
                         R1[1] = pcl_math<real>::f(R2[1], R2[3]);
                     } else {
+#if PCL_RAW_BLOCK_BITS
+                        const uint32_t s1 = small << (8 - j);                        // u[j-1] at bit 31
+                        R1[0] = pcl_fast<real>::gs(R2[0], R2[2], s1 ^ (small << (9 - j)));   // u[j-2] ^ u[j-1]
+                        R1[1] = pcl_fast<real>::gs(R2[1], R2[3], s1);
+#else
                         R1[0] = pcl_fast<real>::gs(R2[0], R2[2], small << 3);
                         R1[1] = pcl_fast<real>::gs(R2[1], R2[3], small << 2);
+#endif
                     }
                     x = pcl_math<real>::f(R1[0], R1[1]);
                 }
@@ -986,7 +1024,9 @@ polar_scl_fast_kernel(PolarParams<real> P)
                     const real sp1 = pcl_fast<real>::softplus_neg_abs(ax1);
                     pm -= (double)(sp + (hard ? ax : (real)0));
                     pm -= (double)(sp1 + (!(x1 >= (real)0) ? ax1 : (real)0));
+#if !PCL_RAW_BLOCK_BITS
                     small &= ~(1u << 30);
+#endif
                     j++;
                     } else {
                     pm -= (double)(sp + (hard ? ax : (real)0));    // DEAD absorbs the penalty
@@ -1131,6 +1171,9 @@ polar_scl_fast_kernel(PolarParams<real> P)
                     P.dbg_parent[(f * N + i0 + j) * LP + p] = (uint8_t)parent;
                 }
 
+#if PCL_RAW_BLOCK_BITS
+                small |= u << (24 + j);
+#else
                 // ---- partial sums: fields of sizes 1, 2, 4 at bits 30, 28, 24 ------------
                 if ((j & 1) == 0) {
                     small = (small & ~(1u << 30)) | (u << 30);
@@ -1148,13 +1191,22 @@ polar_scl_fast_kernel(PolarParams<real> P)
                         }
                     }
                 }
+#endif
             }
+#if PCL_RAW_BLOCK_BITS
+            c8 = small >> 24;                     // u0 .. u7 -> the block's partial sums
+            c8 ^= (c8 >> 1) & 0x55u;
+            c8 ^= (c8 >> 2) & 0x33u;
+            c8 ^= (c8 >> 4) & 0x0fu;
+#else
+            c8 = (((small >> 24) & 15u) ^ c4hi) | (c4hi << 4);
+#endif
             }
 
             // ---- block complete: fold its 8 partial sums upwards while the node is a right child
             // (the last block keeps its fields: the final u-word is assembled from them) -----------
             if (blk != NB - 1) {
-                uint32_t c = (((small >> 24) & 15u) ^ c4hi) | (c4hi << 4);
+                uint32_t c = c8;
                 int s = 8, tt = blk;
                 while ((tt & 1) && s < 32) {
                     const uint32_t left = pcl_bfe(small, 32 - 2 * s, s);
@@ -1222,9 +1274,15 @@ polar_scl_fast_kernel(PolarParams<real> P)
                 for (int w = lane; w < NW; w += 32) {
                     uint32_t v;
                     if (w == NW - 1) {
+#if PCL_RAW_BLOCK_BITS
+                        v = sm;                               // the top byte holds the last block's decisions as they are
+                        v ^= (v >> 1) & 0x00555555u;
+                        v ^= (v >> 2) & 0x00333333u;
+#else
                         v = pcl_bfi(sm, ul, 31, 1);
                         v ^= (v >> 1) & 0x15555555u;
                         v ^= (v >> 2) & 0x03333333u;
+#endif
                         v ^= (v >> 4) & 0x000F0F0Fu;
                         v ^= (v >> 8) & 0x000000FFu;
                     } else {
