@@ -28,7 +28,9 @@ PCL_HOST_DEVICE int pcl_wide_smem_bytes(int LP, int n, int nb)
     off += LP * 4;                     // ulx / pass flags
     off += 2 * (n > 1 ? n - 1 : 1) * LP * 2;    // ptrL[2][n-1][LP]
     off += 2 * (nb > 0 ? nb : 1) * LP * 2;      // ptrB[2][nb][LP]
-    return (off + 15) / 16 * 16;
+    off = (off + 15) / 16 * 16;
+    off += 16;                                  // ctl: vote word of the in-place test
+    return off;
 }
 
 // global scratch of one resident block, in bytes: LLR levels + big left levels + u words of every slot
@@ -56,7 +58,8 @@ __global__ void __launch_bounds__(1024) polar_scl_wide_kernel(PolarParams<real> 
     uint32_t* smallx = (uint32_t*)sm;              sm += LP * 4;
     uint32_t* ulx = (uint32_t*)sm;                 sm += LP * 4;
     uint16_t* ptrL = (uint16_t*)sm;                sm += 2 * nl * LP * 2;
-    uint16_t* ptrB = (uint16_t*)sm;
+    uint16_t* ptrB = (uint16_t*)sm;                sm += 2 * nbb * LP * 2;
+    volatile int* ctl = (volatile int*)(pcl_dyn_smem() + pcl_wide_smem_bytes(LP, n, nb) - 16);
 
     unsigned char* gs = (unsigned char*)P.scratch + (int64_t)blockIdx.x * pcl_wide_scratch_bytes(LP, N, (int)sizeof(real));
     real* gl = (real*)gs;                                              // level d at LP * (N - (N >> (d - 1)))
@@ -151,8 +154,27 @@ __global__ void __launch_bounds__(1024) polar_scl_wide_kernel(PolarParams<real> 
                 cm[p] = m0;
                 cm[LP + p] = m1;
                 smallx[p] = small;
+                // Reliable bit on a full list (the common case): the likely candidates are still in slot order
+                // (strictly, so no tie rule is involved) and every unlikely one lies strictly below the last of
+                // them -> the ranks are the slots, every path continues in place with its likely bit: one vote
+                // instead of the all-pairs ranking, no pointer columns to copy.  Same survivors and slots.
+                const bool full = nact >= L;
+                const double mlik = hard ? m1 : m0, munl = hard ? m0 : m1;
+                if (full) {
+                    newpm[p] = mlik;
+                    if (p == 0) ctl[0] = 1;
+                }
                 __syncthreads();
                 const int ns = (2 * nact < L) ? 2 * nact : L;
+                bool in_place = false;
+                if (full) {
+                    if (p < L && !((p == 0 || newpm[p - 1] > mlik) && munl < newpm[L - 1])) ctl[0] = 0;
+                    __syncthreads();
+                    in_place = ctl[0] != 0;
+                }
+                if (in_place) {
+                    if (act) { pm = mlik; u = hard ? 1u : 0u; }
+                } else {
                 if (act) {
                     // rank of this path's two candidates among the 2 nact live ones: (metric desc, bit asc,
                     // parent asc); an inactive slot holds -inf and can never be ahead of a live candidate
@@ -187,6 +209,7 @@ __global__ void __launch_bounds__(1024) polar_scl_wide_kernel(PolarParams<real> 
                 PL = PLn;
                 PBp = PBn;
                 __syncthreads();
+                }
             }
             if (P.dbg_leaf != nullptr) {
                 P.dbg_leaf[(f * N + i) * LP + p] = x;
