@@ -130,7 +130,7 @@ struct pcl_polar {
     int fpw = 1;                // fast kernel: frames per warp
     int NL = 0, GL = 0;         // fast kernel: compiled-in log2 N and G (0: run-time values)
     int TM = 0;                 // fast kernel, TM variant: one block per SM, mid levels in tensor / shared memory
-    int sc256 = 0;              // list size 1, N = 256, fp32: the register-resident SC kernel (polar_sc.cuh)
+    int sc256 = 0;              // list size 1, N = 256 or 1024, fp32: the register-resident SC kernels (polar_sc.cuh)
     uint32_t* d_uwords[PCL_NSTAGE] = {};   // its decision words [F][8], per host-pipeline stage
     int64_t uwords_cap[PCL_NSTAGE] = {};
     unsigned long long* d_next[PCL_NSTAGE] = {};   // TM variant: ticket counters (one per host-pipeline stage)
@@ -476,7 +476,9 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
         pcl_polar_destroy(h);
         return fail(PCL_ECUDA, "cudaMemcpy failed (tables)");
     }
-    h->sc256 = (list_size == 1 && N == 256 && dtype == PCL_F32 && crc_len == 0 && env_int("PCL_POLAR_SC256", 1) != 0) ? 1 : 0;
+    // list size 1, fp32, bits only: the register-resident SC kernels (polar_sc.cuh) for N = 256 and N = 1024
+    h->sc256 = (list_size == 1 && dtype == PCL_F32 && crc_len == 0 &&
+                ((N == 256 && env_int("PCL_POLAR_SC256", 1) != 0) || (N == 1024 && env_int("PCL_POLAR_SC1024", 1) != 0))) ? 1 : 0;
     if (h->TM || h->sc256) {
         if (cudaMalloc((void**)&h->d_next[0], 8) != cudaSuccess || cudaMemset(h->d_next[0], 0, 8) != cudaSuccess) {
             pcl_polar_destroy(h);
@@ -532,7 +534,7 @@ static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint
         h->d_uwords[stage] = nullptr;
         h->uwords_cap[stage] = 0;
         const int64_t cap = std::max<int64_t>(F, 4096);
-        CUDA_TRY(cudaMalloc((void**)&h->d_uwords[stage], (size_t)cap * 8 * 4));
+        CUDA_TRY(cudaMalloc((void**)&h->d_uwords[stage], (size_t)cap * (h->N / 32) * 4));
         h->uwords_cap[stage] = cap;
     }
     if (!h->d_next[stage]) {
@@ -551,29 +553,34 @@ static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint
     int rc = device_info(&di);
     if (rc) return rc;
     const int wpb = PCL_SC256_WPB;
-    const int smem = wpb * 32 * PCL_SC256_ROW * 4;               // 32 padded frame rows per warp
+    const bool big = h->N == 1024;                               // four length-256 codes in a row (polar_sc1024_kernel)
+    const int NWu = h->N / 32;
+    // 32 padded frame rows per warp (+ the parked partial sums of the N = 1024 kernel)
+    const int smem = wpb * 32 * PCL_SC256_ROW * 4 + (big ? wpb * 32 * PCL_SC1024_BITS * 4 : 0);
     const int bps = std::max(1, di.smem_per_sm / (smem + 1024));
     const int64_t warps_needed = (F + 31) / 32;
     const int grid = (int)std::min<int64_t>((warps_needed + wpb - 1) / wpb, (int64_t)di.sms * bps);
     h->last_grid = grid;
 #ifndef PCL_EMU
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(polar_sc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_TRY(cudaFuncSetAttribute(polar_sc256_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[big]) {
+        const void* kern = big ? (const void*)polar_sc1024_kernel : (const void*)polar_sc256_kernel;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set[big] = true;
     }
 #endif
-    PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, smem, stream, P);
+    if (big) { PCL_LAUNCH(polar_sc1024_kernel, grid, wpb * 32, smem, stream, P); }
+    else { PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, smem, stream, P); }
     CUDA_TRY(cudaGetLastError());
     h->tickets[stage] += (unsigned long long)warps_needed + (unsigned long long)grid * wpb;
 #ifdef PCL_EMU
-    struct Ex { const uint32_t* u; const uint16_t* ip; int64_t F; int NW, K; uint8_t* b; } ex{h->d_uwords[stage], h->d_info_pos, F, 8, h->K, bits_dev};
+    struct Ex { const uint32_t* u; const uint16_t* ip; int64_t F; int NW, K; uint8_t* b; } ex{h->d_uwords[stage], h->d_info_pos, F, NWu, h->K, bits_dev};
     auto run = [](Ex e) { polar_sc_extract_kernel(e.u, e.ip, e.F, e.NW, e.K, e.b); };
     PCL_LAUNCH(run, 2, 256, 0, stream, ex);
 #else
     const int egrid = (int)std::min<int64_t>((F * h->K + 255) / 256, (int64_t)di.sms * 8);
-    polar_sc_extract_kernel<<<egrid, 256, 0, (cudaStream_t)stream>>>(h->d_uwords[stage], h->d_info_pos, F, 8, h->K, bits_dev);
+    polar_sc_extract_kernel<<<egrid, 256, 0, (cudaStream_t)stream>>>(h->d_uwords[stage], h->d_info_pos, F, NWu, h->K, bits_dev);
     CUDA_TRY(cudaGetLastError());
 #endif
     return PCL_OK;

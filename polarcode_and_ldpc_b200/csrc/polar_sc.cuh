@@ -1,6 +1,7 @@
-// polar_sc.cuh -- dedicated successive-cancellation (list size 1) decoder for N = 256, the
+// polar_sc.cuh -- dedicated successive-cancellation (list size 1) decoders for N = 256, the
 // reference's quick-start configuration (BASELINE configs[0]; SCDecoder.decode,
-// /root/reference/src/polar/decoder.py:38-115).
+// /root/reference/src/polar/decoder.py:38-115), and for N = 1024 as four length-256 codes in a row
+// (polar_sc1024_kernel, further down).
 //
 // SC needs no path metric, no prune and no path copies, so the list kernel's machinery is dead
 // weight.  Here a LANE decodes a whole frame and the decoder's entire state lives in registers:
@@ -28,6 +29,15 @@ struct PolarScParams {
     unsigned long long ticket_base;
     int64_t F;
 };
+
+PCL_DEVICE float4 pcl_ldg_f4(const float4* p)
+{
+#ifdef PCL_EMU
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
 
 PCL_DEVICE float sc_g(float a, float b, uint32_t bit_at_31)
 {
@@ -75,6 +85,70 @@ struct sc_node<1> {
 // visit of level 3 reads the channel from there.
 #define PCL_SC256_ROW 260
 #define PCL_SC256_WPB 3
+
+// The eight 32-leaf nodes of a length-256 code whose "channel" row y (256 floats, reference index order) sits in
+// shared memory: decisions go to uw[0 .. 8) (global, decode-step order), X receives the code's 256 partial sums in
+// natural order (the left array a parent level would keep; dead code when the caller ignores it).
+PCL_DEVICE void sc256_decode_row(const float* y, const uint32_t* fzw, uint32_t* uw, bool valid, uint32_t* X)
+{
+    uint32_t b1[4] = {0, 0, 0, 0}, b2[2] = {0, 0}, b3 = 0;
+#pragma unroll 1
+    for (int sb = 0; sb < 8; sb++) {
+        const uint32_t fz = fzw[sb];
+        uint32_t u = 0, c = 0;
+        if (fz != 0xffffffffu) {
+            const int bit1 = sb >> 2, bit2 = (sb >> 1) & 1, bit3 = sb & 1;
+            float R[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                // element k of level 3 <- channel values 8 br5(k) .. + 7 (pairs (0,1) (2,3) (4,5) (6,7) are the
+                // level-1 elements k, k + 64, k + 32, k + 96)
+                const int br = ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+                const float4 v0 = *reinterpret_cast<const float4*>(y + 8 * br);
+                const float4 v1 = *reinterpret_cast<const float4*>(y + 8 * br + 4);
+                float p01, p23, p45, p67, q0, q1;
+                if (bit1) {
+                    p01 = sc_g(v0.x, v0.y, b1[0] << (31 - k));
+                    p23 = sc_g(v0.z, v0.w, b1[2] << (31 - k));
+                    p45 = sc_g(v1.x, v1.y, b1[1] << (31 - k));
+                    p67 = sc_g(v1.z, v1.w, b1[3] << (31 - k));
+                } else {
+                    p01 = pcl_math<float>::f(v0.x, v0.y);
+                    p23 = pcl_math<float>::f(v0.z, v0.w);
+                    p45 = pcl_math<float>::f(v1.x, v1.y);
+                    p67 = pcl_math<float>::f(v1.z, v1.w);
+                }
+                if (bit2) {
+                    q0 = sc_g(p01, p23, b2[0] << (31 - k));
+                    q1 = sc_g(p45, p67, b2[1] << (31 - k));
+                } else {
+                    q0 = pcl_math<float>::f(p01, p23);
+                    q1 = pcl_math<float>::f(p45, p67);
+                }
+                R[k] = bit3 ? sc_g(q0, q1, b3 << (31 - k)) : pcl_math<float>::f(q0, q1);
+            }
+            c = sc_node<32>::run(R, fz, u);
+        }
+        if (valid) uw[sb] = u;
+        // fold the node's partial sums upwards (decoder.py:96-115): a left child parks its word, a right
+        // child combines with its parked sibling and hands the pair on
+        if ((sb & 1) == 0) {
+            b3 = c;
+        } else {
+            const uint32_t x0 = b3 ^ c, x1 = c;                       // level-2 node: 64 bits
+            if ((sb & 2) == 0) {
+                b2[0] = x0; b2[1] = x1;
+            } else if (sb == 3) {                                     // level-1 left node: 128 bits
+                b1[0] = b2[0] ^ x0; b1[1] = b2[1] ^ x1; b1[2] = x0; b1[3] = x1;
+            } else {                                                  // sb == 7: the right node, and with it the whole code
+                const uint32_t r0 = b2[0] ^ x0, r1 = b2[1] ^ x1;
+                X[0] = b1[0] ^ r0; X[1] = b1[1] ^ r1; X[2] = b1[2] ^ x0; X[3] = b1[3] ^ x1;
+                X[4] = r0; X[5] = r1; X[6] = x0; X[7] = x1;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc256_kernel(PolarScParams P)
 {
     constexpr int N = 256;
@@ -97,57 +171,126 @@ __global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc256_kernel(PolarSc
         pcl_cp_async_commit();
         pcl_cp_async_wait<0>();
         __syncwarp();
-        const float* y = rows + lane * PCL_SC256_ROW;
-        uint32_t b1[4] = {0, 0, 0, 0}, b2[2] = {0, 0}, b3 = 0;
-#pragma unroll 1
-        for (int sb = 0; sb < 8; sb++) {
-            const uint32_t fz = P.frozen_words[sb];
-            uint32_t u = 0, c = 0;
-            if (fz != 0xffffffffu) {
-                const int bit1 = sb >> 2, bit2 = (sb >> 1) & 1, bit3 = sb & 1;
-                float R[32];
+        uint32_t X[8];
+        sc256_decode_row(rows + lane * PCL_SC256_ROW, P.frozen_words, P.uwords + (valid ? f : f0) * (N / 32), valid, X);
+    }
+}
+
+// ---- N = 1024: four length-256 codes in a row ---------------------------------------------------------------
+// The two top levels of the tree never exist as arrays.  Quarter q of the code (leaves 256 q ..) is itself a
+// length-256 code whose channel values are the level-2 LLRs of that quarter, and in reference index order those
+// come from FOUR CONSECUTIVE channel LLRs each:  row[j] = op2(op1(llr[4j], llr[4j+1]), op1(llr[4j+2], llr[4j+3])),
+// op1 = f or g by bit 1 of q, op2 by bit 0 -- a sequential, fully coalesced stream, 512 bytes per instruction.
+// So the warp (32 frames, a lane each, as above) makes four passes: all lanes together compute the 32 rows of a
+// quarter into the same padded shared-memory rows the N = 256 kernel uses, then every lane decodes its own row with
+// sc256_decode_row.  What g needs are the partial sums of the quarters already decoded, at natural index br8(j): each
+// lane bit-reverses its frame's 256-bit sums once per quarter (three delta swaps between word pairs and a byte swap)
+// and parks them in shared memory, [frame][24 words]: C = the previous quarter of the same half (level 2), A / B =
+// the two halves of the level-1 left array, (X0 ^ X1, X1).
+PCL_DEVICE void sc_bitrev256(uint32_t* X)
+{
 #pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    // element k of level 3 <- channel values 8 br5(k) .. + 7 (pairs (0,1) (2,3) (4,5) (6,7) are the
-                    // level-1 elements k, k + 64, k + 32, k + 96)
-                    const int br = ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
-                    const float4 v0 = *reinterpret_cast<const float4*>(y + 8 * br);
-                    const float4 v1 = *reinterpret_cast<const float4*>(y + 8 * br + 4);
-                    float p01, p23, p45, p67, q0, q1;
-                    if (bit1) {
-                        p01 = sc_g(v0.x, v0.y, b1[0] << (31 - k));
-                        p23 = sc_g(v0.z, v0.w, b1[2] << (31 - k));
-                        p45 = sc_g(v1.x, v1.y, b1[1] << (31 - k));
-                        p67 = sc_g(v1.z, v1.w, b1[3] << (31 - k));
-                    } else {
-                        p01 = pcl_math<float>::f(v0.x, v0.y);
-                        p23 = pcl_math<float>::f(v0.z, v0.w);
-                        p45 = pcl_math<float>::f(v1.x, v1.y);
-                        p67 = pcl_math<float>::f(v1.z, v1.w);
-                    }
-                    if (bit2) {
-                        q0 = sc_g(p01, p23, b2[0] << (31 - k));
-                        q1 = sc_g(p45, p67, b2[1] << (31 - k));
-                    } else {
-                        q0 = pcl_math<float>::f(p01, p23);
-                        q1 = pcl_math<float>::f(p45, p67);
-                    }
-                    R[k] = bit3 ? sc_g(q0, q1, b3 << (31 - k)) : pcl_math<float>::f(q0, q1);
-                }
-                c = sc_node<32>::run(R, fz, u);
+    for (int w = 0; w < 8; w++) X[w] = __byte_perm(X[w], 0, 0x3120);          // address bits 3 <-> 4
+#pragma unroll
+    for (int i = 0; i < 3; i++) {                                              // address bit i <-> word bit 2 - i
+        const uint32_t m = (i == 0) ? 0x55555555u : (i == 1) ? 0x33333333u : 0x0f0f0f0fu;
+        const int sh = 1 << i, d = 4 >> i;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if ((w & d) == 0) {
+                const uint32_t t = ((X[w] >> sh) ^ X[w + d]) & m;
+                X[w + d] ^= t;
+                X[w] ^= t << sh;
             }
-            if (valid) P.uwords[f * (N / 32) + sb] = u;
-            // fold the node's partial sums upwards (decoder.py:96-115): a left child parks its word, a right
-            // child combines with its parked sibling and hands the pair on
-            if ((sb & 1) == 0) {
-                b3 = c;
-            } else {
-                const uint32_t x0 = b3 ^ c, x1 = c;                       // level-2 node: 64 bits
-                if ((sb & 2) == 0) {
-                    b2[0] = x0; b2[1] = x1;
-                } else if (sb == 3) {                                     // level-1 left node: 128 bits
-                    b1[0] = b2[0] ^ x0; b1[1] = b2[1] ^ x1; b1[2] = x0; b1[3] = x1;
+        }
+    }
+}
+
+#define PCL_SC1024_BITS 24        // words of parked partial sums per frame: C[8], A[8], B[8]
+__global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc1024_kernel(PolarScParams P)
+{
+    constexpr int N = 1024;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* rows = (float*)pcl_dyn_smem() + (size_t)warp * 32 * PCL_SC256_ROW;
+    uint32_t* park = (uint32_t*)((float*)pcl_dyn_smem() + (size_t)(blockDim.x >> 5) * 32 * PCL_SC256_ROW) +
+                     (size_t)warp * 32 * PCL_SC1024_BITS;
+    for (;;) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(P.next, 1ull) - P.ticket_base;
+        tk = pcl_shfl_u64(tk, 0);
+        const int64_t f0 = (int64_t)tk * 32;
+        if (f0 >= P.F) break;
+        const int64_t f = f0 + lane;
+        const bool valid = f < P.F;
+        uint32_t X0[8];
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            __syncwarp();                                        // rows and parked words of the previous quarter are consumed
+            const int bit1 = q >> 1, bit2 = q & 1;
+            // ---- the 32 rows of this quarter: frame r, positions 32 it + lane; the 4 KB of frame r + 1 are in
+            // flight (8 independent 16-byte loads per lane) while frame r is computed ----
+            auto fetch = [&](int r, float4* v) {
+                const int64_t fr = (f0 + r < P.F) ? f0 + r : f0;
+                const float4* src = reinterpret_cast<const float4*>(P.llr + fr * N);
+#pragma unroll
+                for (int it = 0; it < 8; it++) v[it] = pcl_ldg_f4(src + 32 * it + lane);
+            };
+            auto emit = [&](int r, const float4* v) {
+                const uint32_t* pk = park + r * PCL_SC1024_BITS;
+                float* dst = rows + r * PCL_SC256_ROW;
+                uint32_t wa[8], wb[8], wc[8];
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    wc[it] = bit2 ? pk[it] : 0u;
+                    wa[it] = bit1 ? pk[8 + it] : 0u;
+                    wb[it] = bit1 ? pk[16 + it] : 0u;
                 }
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    float a, b;
+                    if (bit1) {
+                        a = sc_g(v[it].x, v[it].y, wa[it] << (31 - lane));
+                        b = sc_g(v[it].z, v[it].w, wb[it] << (31 - lane));
+                    } else {
+                        a = pcl_math<float>::f(v[it].x, v[it].y);
+                        b = pcl_math<float>::f(v[it].z, v[it].w);
+                    }
+                    dst[32 * it + lane] = bit2 ? sc_g(a, b, wc[it] << (31 - lane)) : pcl_math<float>::f(a, b);
+                }
+            };
+            {
+                float4 va[8], vb[8];
+                fetch(0, va);
+#pragma unroll 1
+                for (int r = 0; r < 32; r += 2) {
+                    fetch(r + 1, vb);
+                    emit(r, va);
+                    if (r + 2 < 32) fetch(r + 2, va);
+                    emit(r + 1, vb);
+                }
+            }
+            __syncwarp();
+            // ---- every lane decodes its own row ----
+            uint32_t X[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) X[w] = 0;
+            sc256_decode_row(rows + lane * PCL_SC256_ROW, P.frozen_words + 8 * q, P.uwords + (valid ? f : f0) * (N / 32) + 8 * q,
+                             valid, X);
+            if (q == 3) break;
+            // ---- park what the later quarters need (bit-reversed: position j wants natural index br8(j)) ----
+            sc_bitrev256(X);
+            __syncwarp();                                        // every lane is done with this quarter's rows / words
+            uint32_t* mine = park + lane * PCL_SC1024_BITS;
+            if (q == 0) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) { mine[w] = X[w]; X0[w] = X[w]; }                    // C for quarter 1
+            } else if (q == 1) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) { mine[8 + w] = X0[w] ^ X[w]; mine[16 + w] = X[w]; }   // A, B for quarters 2, 3
+            } else {
+#pragma unroll
+                for (int w = 0; w < 8; w++) mine[w] = X[w];                                        // C for quarter 3
             }
         }
     }

@@ -50,4 +50,6 @@ for dt in ('f32','f64'):
 for N,K,L,F in ((1024,512,16,3),(1024,512,32,2),(2048,1024,8,5)):
     fz=P.bhattacharyya_frozen_set(N,K,2.0); llr=rng.normal(1,3,size=(F,N))
     assert np.array_equal(emu.polar_decode(N,K,L,fz,llr,'f32'),oracle.polar_scl(N,L,fz,llr)),(N,L)
+fz=P.bhattacharyya_frozen_set(1024,512,2.0); llr=rng.normal(1,3,size=(37,1024))
+assert np.array_equal(emu.polar_decode(1024,512,1,fz,llr,'f32'),oracle.polar_sc(1024,fz,llr))     # polar_sc1024_kernel
 print('asan round-2 cases ok')

@@ -289,6 +289,12 @@ inline void sincospif(float x, float* s, float* c) { *s = sinf(3.141592653589793
 inline int __ffs(int v) { return v ? __builtin_ffs(v) : 0; }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xffu) << (8 * i);
+    return r;
+}
 inline unsigned __brev(unsigned v) {
     unsigned r = 0;
     for (int i = 0; i < 32; i++) { r = (r << 1) | (v & 1); v >>= 1; }

@@ -230,6 +230,33 @@ def test_sc_bits_only_sizes(N, K):
     assert int((P.SCDecoder(N, K, frozen_bits=frozen).decode_batch(llr) != ref).any(axis=1).sum()) == 0
 
 
+def test_sc_n1024_dedicated_kernel():
+    """polar_sc1024_kernel (four length-256 codes in a row, a lane per frame): 40 000 frames at -1 / 1 / 3 dB and
+    two rates against the oracle (0 may differ: f and g are exact up to one fp32 rounding of g, decisions
+    are signs), the same bits as the list kernel with L = 1, and the host-buffer path on top of it."""
+    N = 1024
+    tot = bad = 0
+    for K, snr, F in ((512, -1.0, 12000), (512, 1.0, 8000), (512, 3.0, 8000), (768, 3.0, 12000)):
+        frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+        _, llr = _polar_frames(N, K, frozen, F, snr, K + int(10 * snr))
+        ref = oracle.polar_sc(N, frozen, llr, nthreads=oracle.max_threads())
+        dec = P.SCDecoder(N, K, frozen_bits=frozen)
+        assert dec.launch_info()["kernel"] == "polar_sc1024_kernel"
+        dev = torch.from_numpy(llr).cuda().float()
+        got = dec.decode_batch(dev).cpu().numpy()
+        bad += int((got != ref).any(axis=1).sum())
+        tot += F
+        os.environ["PCL_POLAR_SC1024"] = "0"
+        try:
+            dec0 = P.SCDecoder(N, K, frozen_bits=frozen)
+            assert dec0.launch_info()["kernel"] == "polar_scl_fast_kernel"
+            assert np.array_equal(dec0.decode_batch(dev).cpu().numpy(), got)
+        finally:
+            os.environ.pop("PCL_POLAR_SC1024")
+        assert np.array_equal(dec.decode_batch(llr[:777]), ref[:777])          # numpy in -> host pipeline -> int64 out
+    assert tot >= 40000 and bad <= 1e-4 * tot, f"{bad} of {tot} frames differ"
+
+
 def _settled(H, llr, mode, kw, iters):
     """Frames whose reference decode (with early stop) converges within `iters` iterations."""
     kw2 = dict(kw, early_stop=True)

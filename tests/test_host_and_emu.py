@@ -191,6 +191,24 @@ def test_emu_polar_large_code_falls_back_instead_of_failing():
     assert np.array_equal(emu.polar_decode(N, K, 2, fz, llr, "f32", crc=(0x1D, 8)), ref)
 
 
+def test_emu_sc1024_register_resident_kernel():
+    """SC N = 1024 as four length-256 codes in a row (polar_sc1024_kernel): warp-cooperative rows of level-2
+    LLRs, bit-reversed parked partial sums, the N = 256 decoder per lane -- bits of the oracle in both lane
+    orders, with a Bhattacharyya and a random frozen set, and a batch that leaves the last warp partly empty."""
+    N = 1024
+    rng = np.random.default_rng(3)
+    for K, snr, F in ((512, 0.0, 37), (100, -2.0, 33)):
+        fz = P.bhattacharyya_frozen_set(N, K, 2.0) if K != 100 else np.sort(rng.choice(N, N - K, replace=False))
+        np.random.seed(5)
+        llr = P.AWGNChannel(snr).transmit_batch(P.PolarEncoder(N, K, fz).encode_batch(rng.integers(0, 2, size=(F, K))))
+        ref = oracle.polar_sc(N, fz, llr)
+        for reverse in (False, True):
+            got = emu.polar_decode(N, K, 1, fz, llr, "f32", reverse=reverse)
+            assert emu.polar_decode.last_fast == 4 and np.array_equal(got, ref)
+        got = emu.polar_decode(N, K, 1, fz, llr[:5], "f32", env={"PCL_POLAR_SC1024": 0})
+        assert emu.polar_decode.last_fast != 4 and np.array_equal(got, ref[:5])
+
+
 def test_emu_wide_list_and_wide_checks(golden_dir):
     """Beyond a warp's width: list sizes 40 .. 100 through the block-per-frame
     kernel (polar_scl_wide.cuh), both lane orders, CRC selection, and BP checks of degree 44 / 70 through
