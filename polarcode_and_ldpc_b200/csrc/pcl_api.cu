@@ -130,7 +130,7 @@ struct pcl_polar {
     int fpw = 1;                // fast kernel: frames per warp
     int NL = 0, GL = 0;         // fast kernel: compiled-in log2 N and G (0: run-time values)
     int TM = 0;                 // fast kernel, TM variant: one block per SM, mid levels in tensor / shared memory
-    int sc256 = 0;              // list size 1, N = 256 or 1024, fp32: the register-resident SC kernels (polar_sc.cuh)
+    int sc256 = 0;              // list size 1, N = 256 / 512 / 1024 / 2048, fp32: the register-resident SC kernels (polar_sc.cuh)
     uint32_t* d_uwords[PCL_NSTAGE] = {};   // its decision words [F][8], per host-pipeline stage
     int64_t uwords_cap[PCL_NSTAGE] = {};
     unsigned long long* d_next[PCL_NSTAGE] = {};   // TM variant: ticket counters (one per host-pipeline stage)
@@ -476,9 +476,11 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
         pcl_polar_destroy(h);
         return fail(PCL_ECUDA, "cudaMemcpy failed (tables)");
     }
-    // list size 1, fp32, bits only: the register-resident SC kernels (polar_sc.cuh) for N = 256 and N = 1024
+    // list size 1, fp32, bits only: the register-resident SC kernels (polar_sc.cuh) for N = 256 and N = 512 / 1024 / 2048
+    // (PCL_POLAR_SC1024=0: the bigger ones back on the list kernel with L = 1)
     h->sc256 = (list_size == 1 && dtype == PCL_F32 && crc_len == 0 &&
-                ((N == 256 && env_int("PCL_POLAR_SC256", 1) != 0) || (N == 1024 && env_int("PCL_POLAR_SC1024", 1) != 0))) ? 1 : 0;
+                ((N == 256 && env_int("PCL_POLAR_SC256", 1) != 0) ||
+                 ((N == 512 || N == 1024 || N == 2048) && env_int("PCL_POLAR_SC1024", 1) != 0))) ? 1 : 0;
     if (h->TM || h->sc256) {
         if (cudaMalloc((void**)&h->d_next[0], 8) != cudaSuccess || cudaMemset(h->d_next[0], 0, 8) != cudaSuccess) {
             pcl_polar_destroy(h);
@@ -552,25 +554,30 @@ static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc) return rc;
-    const int wpb = PCL_SC256_WPB;
-    const bool big = h->N == 1024;                               // four length-256 codes in a row (polar_sc1024_kernel)
+    const int M = h->N / 256;                                    // M length-256 codes in a row (polar_sc_big_kernel<M>)
+    const bool big = M > 1;
     const int NWu = h->N / 32;
-    // 32 padded frame rows per warp (+ the parked partial sums of the N = 1024 kernel)
-    const int smem = wpb * 32 * PCL_SC256_ROW * 4 + (big ? wpb * 32 * PCL_SC1024_BITS * 4 : 0);
+    // 32 padded frame rows per warp (+ the parked partial sums of the bigger codes: 8 (M - 1) words per frame);
+    // warps per block so that the SM's shared memory is used up: 2 x 3 (N = 256, 1024), 6 (N = 512), 5 (N = 2048)
+    const int wpb = (M == 2) ? 6 : (M == 8) ? 5 : PCL_SC256_WPB;
+    const int smem = wpb * 32 * (PCL_SC256_ROW + (big ? 8 * (M - 1) : 0)) * 4;
     const int bps = std::max(1, di.smem_per_sm / (smem + 1024));
     const int64_t warps_needed = (F + 31) / 32;
     const int grid = (int)std::min<int64_t>((warps_needed + wpb - 1) / wpb, (int64_t)di.sms * bps);
     h->last_grid = grid;
 #ifndef PCL_EMU
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[big]) {
-        const void* kern = big ? (const void*)polar_sc1024_kernel : (const void*)polar_sc256_kernel;
+    static bool attr_set[9] = {};
+    if (!attr_set[M]) {
+        const void* kern = M == 2 ? (const void*)polar_sc_big_kernel<2> : M == 4 ? (const void*)polar_sc_big_kernel<4>
+                         : M == 8 ? (const void*)polar_sc_big_kernel<8> : (const void*)polar_sc256_kernel;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set[big] = true;
+        attr_set[M] = true;
     }
 #endif
-    if (big) { PCL_LAUNCH(polar_sc1024_kernel, grid, wpb * 32, smem, stream, P); }
+    if (M == 2) { PCL_LAUNCH(polar_sc_big_kernel<2>, grid, wpb * 32, smem, stream, P); }
+    else if (M == 4) { PCL_LAUNCH(polar_sc_big_kernel<4>, grid, wpb * 32, smem, stream, P); }
+    else if (M == 8) { PCL_LAUNCH(polar_sc_big_kernel<8>, grid, wpb * 32, smem, stream, P); }
     else { PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, smem, stream, P); }
     CUDA_TRY(cudaGetLastError());
     h->tickets[stage] += (unsigned long long)warps_needed + (unsigned long long)grid * wpb;

@@ -1,7 +1,7 @@
 // polar_sc.cuh -- dedicated successive-cancellation (list size 1) decoders for N = 256, the
 // reference's quick-start configuration (BASELINE configs[0]; SCDecoder.decode,
 // /root/reference/src/polar/decoder.py:38-115), and for N = 1024 as four length-256 codes in a row
-// (polar_sc1024_kernel, further down).
+// (N = 512 / 1024 / 2048: polar_sc_big_kernel<M>, further down).
 //
 // SC needs no path metric, no prune and no path copies, so the list kernel's machinery is dead
 // weight.  Here a LANE decodes a whole frame and the decoder's entire state lives in registers:
@@ -31,6 +31,15 @@ struct PolarScParams {
 };
 
 PCL_DEVICE float4 pcl_ldg_f4(const float4* p)
+{
+#ifdef PCL_EMU
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
+
+PCL_DEVICE float2 pcl_ldg_f2(const float2* p)
 {
 #ifdef PCL_EMU
     return *p;
@@ -206,15 +215,28 @@ PCL_DEVICE void sc_bitrev256(uint32_t* X)
     }
 }
 
-#define PCL_SC1024_BITS 24        // words of parked partial sums per frame: C[8], A[8], B[8]
-__global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc1024_kernel(PolarScParams P)
+
+// ---- N = 256 M, M = 2 / 4 / 8: M length-256 codes in a row ----------------------------------------------------
+// The m = log2 M top levels never exist as arrays: sub-block q is a length-256 code whose channel values, in
+// reference index order, come from M CONSECUTIVE channel LLRs each through a tree of adjacent pairs -- level l
+// (1 = top) combines e[2t], e[2t+1] with f or g by bit (m - l) of q.  The partial sums g needs are the level-l
+// LEFT array of the node that contains q: 2^(m-l) chunks of 256 bits, element t reading chunk rev(t) at natural
+// index br8(j).  Every lane keeps its frame's left arrays bit-reversed inside each chunk (so position j reads bit j)
+// in shared memory, [frame][8 (M - 1) words]: level l at word 8 (2^(m-l) - 1); after a sub-block the lane folds its
+// 256 new sums upwards through the parked arrays -- (left ^ right, right) chunk by chunk -- until it meets a level
+// where the node is a left child, and parks them there.  M = 4 is the N = 1024 layout described above.
+template <int M>
+__global__ void __launch_bounds__(M == 4 ? 96 : 192) polar_sc_big_kernel(PolarScParams P)
 {
-    constexpr int N = 1024;
+    constexpr int m = (M == 2) ? 1 : (M == 4) ? 2 : 3;
+    constexpr int N = 256 * M;
+    constexpr int PW = 8 * (M - 1);                  // parked words per frame
+    constexpr int U = 32 / M;                        // lane-positions per pipeline stage (32 floats per lane)
+    static_assert(M == 2 || M == 4 || M == 8, "256 M with M = 2, 4, 8");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float* rows = (float*)pcl_dyn_smem() + (size_t)warp * 32 * PCL_SC256_ROW;
-    uint32_t* park = (uint32_t*)((float*)pcl_dyn_smem() + (size_t)(blockDim.x >> 5) * 32 * PCL_SC256_ROW) +
-                     (size_t)warp * 32 * PCL_SC1024_BITS;
+    uint32_t* park = (uint32_t*)((float*)pcl_dyn_smem() + (size_t)(blockDim.x >> 5) * 32 * PCL_SC256_ROW) + (size_t)warp * 32 * PW;
     for (;;) {
         unsigned long long tk = 0;
         if (lane == 0) tk = atomicAdd(P.next, 1ull) - P.ticket_base;
@@ -223,51 +245,82 @@ __global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc1024_kernel(PolarS
         if (f0 >= P.F) break;
         const int64_t f = f0 + lane;
         const bool valid = f < P.F;
-        uint32_t X0[8];
 #pragma unroll 1
-        for (int q = 0; q < 4; q++) {
-            __syncwarp();                                        // rows and parked words of the previous quarter are consumed
-            const int bit1 = q >> 1, bit2 = q & 1;
-            // ---- the 32 rows of this quarter: frame r, positions 32 it + lane; the 4 KB of frame r + 1 are in
-            // flight (8 independent 16-byte loads per lane) while frame r is computed ----
-            auto fetch = [&](int r, float4* v) {
-                const int64_t fr = (f0 + r < P.F) ? f0 + r : f0;
-                const float4* src = reinterpret_cast<const float4*>(P.llr + fr * N);
+        for (int q = 0; q < M; q++) {
+            __syncwarp();                            // rows and parked words of the previous sub-block are consumed / written
+            // ---- the 32 rows of this sub-block.  Lane-position lp = 8 r + it: frame r, position j = 32 it + lane,
+            // M consecutive floats at M j; stage s + 1 is in flight while stage s is computed ----
+            auto fetch = [&](int st, float* v) {
 #pragma unroll
-                for (int it = 0; it < 8; it++) v[it] = pcl_ldg_f4(src + 32 * it + lane);
+                for (int g8 = 0; g8 < (U + 7) / 8; g8++) {               // one frame per group of up to 8 lane-positions
+                    const int lp0 = st * U + 8 * g8, r = lp0 >> 3, it0 = lp0 & 7;
+                    const int64_t fr = (f0 + r < P.F) ? f0 + r : f0;
+                    const float* src = P.llr + fr * N + M * (32 * it0 + lane);
+#pragma unroll
+                    for (int i = 0; i < (U < 8 ? U : 8); i++) {
+                        float* o = v + M * (8 * g8 + i);
+                        if (M == 2) {
+                            const float2 t = pcl_ldg_f2(reinterpret_cast<const float2*>(src + M * 32 * i));
+                            o[0] = t.x; o[1] = t.y;
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < M / 4; h++) {
+                                const float4 t = pcl_ldg_f4(reinterpret_cast<const float4*>(src + M * 32 * i) + h);
+                                o[4 * h] = t.x; o[4 * h + 1] = t.y; o[4 * h + 2] = t.z; o[4 * h + 3] = t.w;
+                            }
+                        }
+                    }
+                }
             };
-            auto emit = [&](int r, const float4* v) {
-                const uint32_t* pk = park + r * PCL_SC1024_BITS;
-                float* dst = rows + r * PCL_SC256_ROW;
-                uint32_t wa[8], wb[8], wc[8];
+            auto emit = [&](int st, const float* v) {
+                // the words g reads, shifted so that this lane's bit sits at bit 31: level l, result t -> chunk rev(t)
+                uint32_t wsh[U][M - 1];
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    wc[it] = bit2 ? pk[it] : 0u;
-                    wa[it] = bit1 ? pk[8 + it] : 0u;
-                    wb[it] = bit1 ? pk[16 + it] : 0u;
+                for (int i = 0; i < U; i++) {
+                    const int lp = st * U + i, r = lp >> 3, it = lp & 7;
+                    const uint32_t* pk = park + r * PW + it;
+                    int idx = 0;
+#pragma unroll
+                    for (int l = 1; l <= m; l++) {
+                        const bool isg = (q >> (m - l)) & 1;
+#pragma unroll
+                        for (int t = 0; t < (M >> l); t++, idx++) {
+                            int c = 0;
+#pragma unroll
+                            for (int bb = 0; bb < m - l; bb++) c |= ((t >> bb) & 1) << (m - l - 1 - bb);
+                            wsh[i][idx] = isg ? (pk[8 * ((1 << (m - l)) - 1) + 8 * c] << (31 - lane)) : 0u;
+                        }
+                    }
                 }
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    float a, b;
-                    if (bit1) {
-                        a = sc_g(v[it].x, v[it].y, wa[it] << (31 - lane));
-                        b = sc_g(v[it].z, v[it].w, wb[it] << (31 - lane));
-                    } else {
-                        a = pcl_math<float>::f(v[it].x, v[it].y);
-                        b = pcl_math<float>::f(v[it].z, v[it].w);
+                for (int i = 0; i < U; i++) {
+                    const int lp = st * U + i, r = lp >> 3, it = lp & 7;
+                    float e[M];
+#pragma unroll
+                    for (int t = 0; t < M; t++) e[t] = v[M * i + t];
+                    int idx = 0;
+#pragma unroll
+                    for (int l = 1; l <= m; l++) {                       // level l: M >> l results from adjacent pairs
+                        const bool isg = (q >> (m - l)) & 1;
+#pragma unroll
+                        for (int t = 0; t < (M >> l); t++, idx++) {
+                            if (isg) e[t] = sc_g(e[2 * t], e[2 * t + 1], wsh[i][idx]);
+                            else e[t] = pcl_math<float>::f(e[2 * t], e[2 * t + 1]);
+                        }
                     }
-                    dst[32 * it + lane] = bit2 ? sc_g(a, b, wc[it] << (31 - lane)) : pcl_math<float>::f(a, b);
+                    rows[r * PCL_SC256_ROW + 32 * it + lane] = e[0];
                 }
             };
             {
-                float4 va[8], vb[8];
+                constexpr int NST = 256 / U;                             // stages per sub-block
+                float va[32], vb[32];
                 fetch(0, va);
 #pragma unroll 1
-                for (int r = 0; r < 32; r += 2) {
-                    fetch(r + 1, vb);
-                    emit(r, va);
-                    if (r + 2 < 32) fetch(r + 2, va);
-                    emit(r + 1, vb);
+                for (int st = 0; st < NST; st += 2) {
+                    fetch(st + 1, vb);
+                    emit(st, va);
+                    if (st + 2 < NST) fetch(st + 2, va);
+                    emit(st + 1, vb);
                 }
             }
             __syncwarp();
@@ -277,20 +330,34 @@ __global__ void __launch_bounds__(32 * PCL_SC256_WPB) polar_sc1024_kernel(PolarS
             for (int w = 0; w < 8; w++) X[w] = 0;
             sc256_decode_row(rows + lane * PCL_SC256_ROW, P.frozen_words + 8 * q, P.uwords + (valid ? f : f0) * (N / 32) + 8 * q,
                              valid, X);
-            if (q == 3) break;
-            // ---- park what the later quarters need (bit-reversed: position j wants natural index br8(j)) ----
+            if (q == M - 1) break;
+            // ---- fold the new sums upwards and park them (own frame only: no barrier needed before the next staging
+            // except the one at the top of the loop) ----
             sc_bitrev256(X);
-            __syncwarp();                                        // every lane is done with this quarter's rows / words
-            uint32_t* mine = park + lane * PCL_SC1024_BITS;
-            if (q == 0) {
+            uint32_t* mine = park + lane * PW;
+            uint32_t cur[8 * (M / 2)];
 #pragma unroll
-                for (int w = 0; w < 8; w++) { mine[w] = X[w]; X0[w] = X[w]; }                    // C for quarter 1
-            } else if (q == 1) {
+            for (int w = 0; w < 8; w++) cur[w] = X[w];
+            bool done = false;
 #pragma unroll
-                for (int w = 0; w < 8; w++) { mine[8 + w] = X0[w] ^ X[w]; mine[16 + w] = X[w]; }   // A, B for quarters 2, 3
-            } else {
+            for (int l = m; l >= 1; l--) {
+                const int nch = 1 << (m - l);                            // chunks of the node at this level (compile time after unrolling)
+                const int off = 8 * (nch - 1);
+                if (!done) {
+                    if (((q >> (m - l)) & 1) == 0) {                     // left child: park
 #pragma unroll
-                for (int w = 0; w < 8; w++) mine[w] = X[w];                                        // C for quarter 3
+                        for (int w = 0; w < 8 * (M / 2); w++)
+                            if (w < 8 * nch) mine[off + w] = cur[w];
+                        done = true;
+                    } else if (l > 1) {                                  // right child: (left ^ right, right), twice the chunks
+#pragma unroll
+                        for (int w = 0; w < 8 * (M / 2); w++)
+                            if (w < 8 * nch && 8 * nch + w < 8 * (M / 2)) {
+                                cur[8 * nch + w] = cur[w];
+                                cur[w] ^= mine[off + w];
+                            }
+                    }
+                }
             }
         }
     }

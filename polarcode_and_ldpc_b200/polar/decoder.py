@@ -117,8 +117,10 @@ class _PolarBase:
         _native.check(_native.lib().pcl_polar_launch_info(self._h, ctypes.byref(g), ctypes.byref(b),
                                                           ctypes.byref(s), ctypes.byref(lv), ctypes.byref(fa)))
         if fa.value == 4:
-            return {"grid": g.value, "block": 96, "smem_bytes": 3 * 32 * (260 + (24 if self.N == 1024 else 0)) * 4, "global_levels": 0,
-                    "kernel": "polar_sc1024_kernel" if self.N == 1024 else "polar_sc256_kernel",
+            M = self.N // 256
+            wpb = {2: 6, 8: 5}.get(M, 3)
+            return {"grid": g.value, "block": 32 * wpb, "smem_bytes": wpb * 32 * (260 + (8 * (M - 1) if M > 1 else 0)) * 4, "global_levels": 0,
+                    "kernel": "polar_sc256_kernel" if M == 1 else "polar_sc_big_kernel",
                     "lanes_per_path": 1, "frames_per_warp": 32, "compiled_code_length": True, "tensor_memory": False}
         if fa.value == 5:
             return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "global_levels": lv.value,

@@ -230,8 +230,26 @@ def test_sc_bits_only_sizes(N, K):
     assert int((P.SCDecoder(N, K, frozen_bits=frozen).decode_batch(llr) != ref).any(axis=1).sum()) == 0
 
 
+@pytest.mark.parametrize("N,K", [(512, 256), (2048, 1024), (2048, 1500)])
+def test_sc_big_kernel_other_sizes(N, K):
+    """polar_sc_big_kernel<2> / <8>: 2 and 8 length-256 codes in a row; against the oracle and the list kernel."""
+    frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
+    _, llr = _polar_frames(N, K, frozen, 8000, 1.0, N + K)
+    ref = oracle.polar_sc(N, frozen, llr, nthreads=oracle.max_threads())
+    dec = P.SCDecoder(N, K, frozen_bits=frozen)
+    assert dec.launch_info()["kernel"] == "polar_sc_big_kernel"
+    dev = torch.from_numpy(llr).cuda().float()
+    got = dec.decode_batch(dev).cpu().numpy()
+    assert int((got != ref).any(axis=1).sum()) == 0
+    os.environ["PCL_POLAR_SC1024"] = "0"
+    try:
+        assert np.array_equal(P.SCDecoder(N, K, frozen_bits=frozen).decode_batch(dev).cpu().numpy(), got)
+    finally:
+        os.environ.pop("PCL_POLAR_SC1024")
+
+
 def test_sc_n1024_dedicated_kernel():
-    """polar_sc1024_kernel (four length-256 codes in a row, a lane per frame): 40 000 frames at -1 / 1 / 3 dB and
+    """polar_sc_big_kernel<4> (four length-256 codes in a row, a lane per frame): 40 000 frames at -1 / 1 / 3 dB and
     two rates against the oracle (0 may differ: f and g are exact up to one fp32 rounding of g, decisions
     are signs), the same bits as the list kernel with L = 1, and the host-buffer path on top of it."""
     N = 1024
@@ -241,7 +259,7 @@ def test_sc_n1024_dedicated_kernel():
         _, llr = _polar_frames(N, K, frozen, F, snr, K + int(10 * snr))
         ref = oracle.polar_sc(N, frozen, llr, nthreads=oracle.max_threads())
         dec = P.SCDecoder(N, K, frozen_bits=frozen)
-        assert dec.launch_info()["kernel"] == "polar_sc1024_kernel"
+        assert dec.launch_info()["kernel"] == "polar_sc_big_kernel"
         dev = torch.from_numpy(llr).cuda().float()
         got = dec.decode_batch(dev).cpu().numpy()
         bad += int((got != ref).any(axis=1).sum())

@@ -192,13 +192,13 @@ def test_emu_polar_large_code_falls_back_instead_of_failing():
 
 
 def test_emu_sc1024_register_resident_kernel():
-    """SC N = 1024 as four length-256 codes in a row (polar_sc1024_kernel): warp-cooperative rows of level-2
-    LLRs, bit-reversed parked partial sums, the N = 256 decoder per lane -- bits of the oracle in both lane
-    orders, with a Bhattacharyya and a random frozen set, and a batch that leaves the last warp partly empty."""
-    N = 1024
+    """SC N = 512 / 1024 / 2048 as 2 / 4 / 8 length-256 codes in a row (polar_sc_big_kernel<M>): warp-cooperative
+    rows of level-m LLRs, bit-reversed parked partial sums folded upwards per frame, the N = 256 decoder per lane --
+    bits of the oracle in both lane orders, with Bhattacharyya and random frozen sets, batches that leave the last
+    warp partly empty."""
     rng = np.random.default_rng(3)
-    for K, snr, F in ((512, 0.0, 37), (100, -2.0, 33)):
-        fz = P.bhattacharyya_frozen_set(N, K, 2.0) if K != 100 else np.sort(rng.choice(N, N - K, replace=False))
+    for N, K, snr, F in ((1024, 512, 0.0, 37), (1024, 100, -2.0, 33), (512, 256, 0.0, 35), (2048, 1024, 0.5, 33), (2048, 300, -2.0, 33)):
+        fz = P.bhattacharyya_frozen_set(N, K, 2.0) if 2 * K == N else np.sort(rng.choice(N, N - K, replace=False))
         np.random.seed(5)
         llr = P.AWGNChannel(snr).transmit_batch(P.PolarEncoder(N, K, fz).encode_batch(rng.integers(0, 2, size=(F, K))))
         ref = oracle.polar_sc(N, fz, llr)
