@@ -51,5 +51,8 @@ for N,K,L,F in ((1024,512,16,3),(1024,512,32,2),(2048,1024,8,5)):
     fz=P.bhattacharyya_frozen_set(N,K,2.0); llr=rng.normal(1,3,size=(F,N))
     assert np.array_equal(emu.polar_decode(N,K,L,fz,llr,'f32'),oracle.polar_scl(N,L,fz,llr)),(N,L)
 fz=P.bhattacharyya_frozen_set(1024,512,2.0); llr=rng.normal(1,3,size=(37,1024))
-assert np.array_equal(emu.polar_decode(1024,512,1,fz,llr,'f32'),oracle.polar_sc(1024,fz,llr))     # polar_sc1024_kernel
+assert np.array_equal(emu.polar_decode(1024,512,1,fz,llr,'f32'),oracle.polar_sc(1024,fz,llr))     # polar_sc_big_kernel<4>
+for N2 in (512, 2048):
+    fz=P.bhattacharyya_frozen_set(N2,N2//2,2.0); llr=rng.normal(1,3,size=(33,N2))
+    assert np.array_equal(emu.polar_decode(N2,N2//2,1,fz,llr,'f32'),oracle.polar_sc(N2,fz,llr))   # polar_sc_big_kernel<2>, <8>
 print('asan round-2 cases ok')
