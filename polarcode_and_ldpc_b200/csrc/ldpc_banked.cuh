@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(COOP ? 256 : 1024) ldpc_banked_kernel(LdpcPara
         else __syncwarp();
     };
 
+    for (int s = tid; s < NS; s += T) msg[s] = 0.0f;                   // the words of empty check seats stay zero from here on
+    sync();
     for (;;) {
         unsigned long long fq = 0;
         if (coop) {
@@ -94,9 +96,16 @@ __global__ void __launch_bounds__(COOP ? 256 : 1024) ldpc_banked_kernel(LdpcPara
             sllr[pi] = (v != 0xffff) ? ch[v] * (MODE == 0 ? 1.4426950408889634f : 1.0f) : 0.0f;
         }
         sync();
-        for (int s = tid; s < NS; s += T) {                            // decoder.py:144-146
-            const int cp = P.cpos[s];
-            msg[s] = (cp != 0xffff) ? sllr[cp] : 0.0f;
+        // decoder.py:144-146: every edge starts with its variable's channel value -- scattered from position
+        // space through the same byte-offset table the variable pass uses (an empty position writes its zero to
+        // the zero words of an empty seat; those were cleared once, before the first frame, and stay zero)
+        for (int pi = tid; pi < NP; pi += T) {
+            const unsigned long long pk = P.bpack[pi];
+            const uint32_t plo = (uint32_t)pk;
+            const float c = sllr[pi];
+            pcl_sts_f32(msg_s + (plo & 0xffffu), c);
+            pcl_sts_f32(msg_s + (plo >> 16), c);
+            pcl_sts_f32(msg_s + (uint32_t)(pk >> 32), c);
         }
         sync();
 
