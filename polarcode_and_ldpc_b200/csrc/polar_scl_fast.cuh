@@ -1042,11 +1042,11 @@ polar_scl_fast_kernel(PolarParams<real> P)
                         kb = hard ? base : other;                  // bit 1
                         if (!act) { ka = DEAD; kb = DEAD; }
                     } else {
-                        // ka: the likely bit (u = hard), kb: the other one; ids carry (bit, parent)
-                        const double base = pm - (double)sp;
-                        const int ida = (hard ? LP : 0) | p;
-                        ka = pcl_prune_key<NC>(base, ida);
-                        kb = pcl_prune_key<NC>(base - (double)ax, ida ^ LP);
+                        // ka: the likely bit (u = hard), kb: the other one.  The ids (bit, parent) go into the lowest
+                        // mantissa bits only when the list really has to be ranked (below): the in-place test reads the
+                        // high words, and a path that continues in place keeps its metric untouched.
+                        ka = pm - (double)sp;
+                        kb = ka - (double)ax;
                     }
                     bool in_place = false;        // every survivor is its own parent's likely bit, same slot
                     if (!EXACT && PCL_PRUNE_QUICK && nact >= L) {
@@ -1071,6 +1071,11 @@ polar_scl_fast_kernel(PolarParams<real> P)
 #endif
                     }
                     if (!in_place) {
+                    if (!EXACT) {
+                        const int ida = (hard ? LP : 0) | p;
+                        ka = pcl_prune_key<NC>(ka, ida);
+                        kb = pcl_prune_key<NC>(kb, ida ^ LP);
+                    }
                     double2 kv;
                     kv.x = ka;
                     kv.y = kb;
