@@ -728,6 +728,13 @@ static int ldpc_with_kernel_c(pcl_ldpc* h, Fn&& fn)
     if constexpr (sizeof(real) == 4) {
         if (h->lay.banked) {
             if (h->lay.paired) {
+                if constexpr (COOP == 0) {
+                    // 16 variable positions per lane (n = 481 .. 512) and at most 28 warps per block: channel values in registers
+                    if (h->lay.NP == 512 && h->wpb <= 28 && env_int("PCL_LDPC_REGLLR", 1) != 0) {
+                        if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, 0, 1, 16>);
+                        return fn(ldpc_banked_kernel<0, 6, 0, 1, 16>);
+                    }
+                }
                 if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, COOP, 1>);
                 return fn(ldpc_banked_kernel<0, 6, COOP, 1>);
             }
