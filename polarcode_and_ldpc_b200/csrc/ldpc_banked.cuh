@@ -48,9 +48,10 @@ PCL_DEVICE void pcl_sts_f32(pcl_saddr a, float v) { asm volatile("st.shared.f32 
 // One warp per frame (COOP = 0): the library launches ONE block per SM holding every warp the SM's
 // shared memory has room for (up to 32), so the residency cannot depend on which shared-memory /
 // L1 split the SM happens to be in when the grid arrives.
-// NPR > 0 (warp-per-frame mode, NP == 32 NPR, at most 28 warps per block): a lane keeps the channel values of its NPR
-// variable positions in registers for the whole decode (72 registers instead of 55; 16 shared-memory reads and their
-// address arithmetic less per iteration: BP n = 504 10.91 -> 11.12 Gbps).
+// NPR > 0 (every lane owns exactly NPR variable positions: NP == 32 NPR in the warp-per-frame mode with at most 28 warps
+// per block, NP == 128 NPR in the block-per-frame mode): a lane keeps the channel values of its positions in registers
+// for the whole decode (72 registers instead of 55; NPR shared-memory reads and their address arithmetic less per
+// iteration: BP n = 504 10.91 -> 11.12 Gbps).
 template <int MODE, int DC, int COOP, int PAIRED, int NPR = 0>
 __global__ void __launch_bounds__(COOP ? 256 : (NPR ? 896 : 1024)) ldpc_banked_kernel(LdpcParams<float> P)
 {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(COOP ? 256 : (NPR ? 896 : 1024)) ldpc_banked_k
         float cl[NPR > 0 ? NPR : 1];
         if (NPR > 0) {
 #pragma unroll
-            for (int r = 0; r < NPR; r++) cl[r] = sllr[32 * r + lane];
+            for (int r = 0; r < NPR; r++) cl[r] = sllr[32 * (w0 + wstep * r) + lane];
         }
         sync();
 
@@ -217,9 +218,9 @@ __global__ void __launch_bounds__(COOP ? 256 : (NPR ? 896 : 1024)) ldpc_banked_k
                     for (int r4 = 0; r4 < NPR; r4 += 4) {
                         unsigned long long k4[4];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) k4[e] = P.bpack[32 * (r4 + e) + lane];
+                        for (int e = 0; e < 4; e++) k4[e] = P.bpack[32 * (w0 + wstep * (r4 + e)) + lane];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) one(32 * (r4 + e), k4[e], cl[r4 + e], true);
+                        for (int e = 0; e < 4; e++) one(32 * (w0 + wstep * (r4 + e)), k4[e], cl[r4 + e], true);
                     }
                     return;
                 }

@@ -729,7 +729,8 @@ static int ldpc_with_kernel_c(pcl_ldpc* h, Fn&& fn)
         if (h->lay.banked) {
             if (h->lay.paired) {
                 if constexpr (COOP == 0) {
-                    // 16 variable positions per lane (n = 481 .. 512) and at most 28 warps per block: channel values in registers
+                    // 16 variable positions per lane (n = 481 .. 512) and at most 28 warps per block: channel values in
+                    // registers (ldpc_banked.cuh, NPR; the block-per-frame mode measured no gain: 10.59 vs 10.58 Gbps at n = 2016)
                     if (h->lay.NP == 512 && h->wpb <= 28 && env_int("PCL_LDPC_REGLLR", 1) != 0) {
                         if (h->mode == PCL_LDPC_MS) return fn(ldpc_banked_kernel<1, 6, 0, 1, 16>);
                         return fn(ldpc_banked_kernel<0, 6, 0, 1, 16>);
