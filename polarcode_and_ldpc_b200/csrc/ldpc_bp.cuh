@@ -401,6 +401,32 @@ template <typename real, int DMAX>
 PCL_DEVICE void cn_ms_core(const real* x, real* out, real norm)
 {
     typedef typename ldpc_bits<real>::u bits_t;
+    if constexpr (sizeof(real) == 4 && DMAX == 6) {
+        // fp32, degree 6: the six leave-one-out minima straight from 3-input minima (FMNMX3 with |.| operands on
+        // sm_100: nvcc fuses the nested fminf) -- two group minima and one 3-input minimum per edge, 8 instructions
+        // instead of the min / second-min ladder and a compare-select per edge (30).  Signs travel as raw sign
+        // bits: a -0.0 among the others makes their minimum 0, so the sign of that zero is all it can change.
+        uint32_t xb[6], sall = 0;
+        float a[6], mn[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            xb[j] = __float_as_uint((float)x[j]);
+            a[j] = fabsf((float)x[j]);
+            sall ^= xb[j];
+        }
+        const float t012 = fminf(fminf(a[0], a[1]), a[2]), t345 = fminf(fminf(a[3], a[4]), a[5]);
+        mn[0] = fminf(fminf(a[1], a[2]), t345);
+        mn[1] = fminf(fminf(a[0], a[2]), t345);
+        mn[2] = fminf(fminf(a[0], a[1]), t345);
+        mn[3] = fminf(fminf(a[4], a[5]), t012);
+        mn[4] = fminf(fminf(a[3], a[5]), t012);
+        mn[5] = fminf(fminf(a[3], a[4]), t012);
+        // the sign rides on the normalisation factor: min * (+-norm), one LOP3 and one FMUL per edge ((+-1 * min) * norm, :285)
+        const uint32_t sn = (sall & 0x80000000u) ^ __float_as_uint((float)norm);
+#pragma unroll
+        for (int i = 0; i < 6; i++) out[i] = (real)(mn[i] * __uint_as_float(sn ^ (xb[i] & 0x80000000u)));
+        return;
+    }
     real a[DMAX];
     bits_t sall = 0;
     real m1 = pcl_math<real>::inf(), m2 = pcl_math<real>::inf();
