@@ -954,7 +954,11 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
         int coop = env_int("PCL_LDPC_COOP", -1);
         if (coop < 0) coop = resident < 16 ? 1 : 0;
         Y.coop = coop ? 1 : 0;
-        if (Y.coop) h->wpb = 4;
+        if (Y.coop) {
+            // warps per frame: 4, or 8 for the largest codes (Min-Sum n = 2016: 9.8 / 11.7 / 11.9 Gbps at 2 / 4 / 8)
+            h->wpb = env_int("PCL_LDPC_COOP_WPB", n >= 1985 ? 8 : 4);
+            if (h->wpb != 2 && h->wpb != 8) h->wpb = 4;
+        }
     }
     if (!Y.coop && Y.banked && env_int("PCL_LDPC_FAT", 1) != 0 && env_int("PCL_LDPC_WPB", 0) < 1) {
         // warp-per-frame banked kernel: one fat block per SM when a single block can hold everything the
