@@ -313,14 +313,19 @@ __global__ void __launch_bounds__(M == 4 ? 96 : 192) polar_sc_big_kernel(PolarSc
             };
             {
                 constexpr int NST = 256 / U;                             // stages per sub-block
-                float va[32], vb[32];
+                // two stages (2 x 32 floats per lane, 8 KB per warp) in flight while a third is combined: the ncu capture
+                // of the two-buffer version showed 6 warps per SM waiting on these loads (long_scoreboard 1.7 cycles / issue)
+                float va[32], vb[32], vc[32];
                 fetch(0, va);
+                fetch(1, vb);
 #pragma unroll 1
-                for (int st = 0; st < NST; st += 2) {
-                    fetch(st + 1, vb);
+                for (int st = 0; st < NST; st += 3) {
+                    if (st + 2 < NST) fetch(st + 2, vc);
                     emit(st, va);
-                    if (st + 2 < NST) fetch(st + 2, va);
-                    emit(st + 1, vb);
+                    if (st + 3 < NST) fetch(st + 3, va);
+                    if (st + 1 < NST) emit(st + 1, vb);
+                    if (st + 4 < NST) fetch(st + 4, vb);
+                    if (st + 2 < NST) emit(st + 2, vc);
                 }
             }
             __syncwarp();
