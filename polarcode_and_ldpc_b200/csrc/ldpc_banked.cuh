@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(COOP ? 256 : (NPR ? 896 : 1024)) ldpc_banked_k
         else __syncwarp();
     };
 
-    for (int s = tid; s < NS; s += T) msg[s] = 0.0f;                   // the words of empty check seats stay zero from here on
+    for (int s = tid; s < NS; s += T) msg[s] = 0.0f;                   // the words of empty check seats stay (numerically) zero from here on
     sync();
     for (;;) {
         unsigned long long fq = 0;

@@ -887,8 +887,9 @@ extern "C" int pcl_ldpc_create(pcl_ldpc_t** out, int m, int n, const uint8_t* H,
             // Device form of the per-position table: BYTE offsets of the three message words (the variable
             // pass adds them to the frame's base, no shifts).  An empty position points at words of an EMPTY
             // check seat instead of carrying a flag the kernel would have to branch on: such words start at
-            // zero, the check rule maps six zeros to six zeros, and a position whose channel value is zero
-            // writes zeros back, so they stay zero for the whole decode.  (A (3, 6) code with empty positions
+            // zero, the check rule maps six zeros to six zeros (the paired BP rule: to lg2 of a ratio that is 1
+            // up to rounding, ~1e-7), and a position whose channel value is zero writes their sums back, so they
+            // stay at that level for the whole decode and no real variable ever reads them.  (A (3, 6) code with empty positions
             // always has an empty seat: n = 2 m.)  The word is taken from a bank the fetch leaves free when
             // there is one; otherwise that fetch costs one more wavefront.
             Y.NS = bl.NS;
