@@ -56,7 +56,8 @@ int pcl_device_count(void);
  * equal the number of zeros.  list_size 1 with want_metric 0 is the SC decoder.
  * crc_len 0 disables CRC-aided selection (the reference never applies it,
  * decoder.py:259); otherwise crc_poly/crc_len follow src/polar/utils.py:128-163.
- * Limits (PCL_EUNSUPPORTED beyond): N <= 8192, list_size <= 1024.
+ * Limits (PCL_EUNSUPPORTED beyond): N <= 65536 (16-bit leaf positions; a configuration whose per-frame bit arrays
+ * do not fit one block's shared memory is refused at creation), list_size <= 1024.
  */
 int pcl_polar_create(pcl_polar_t** out, int N, int K, int list_size, const uint8_t* frozen_mask,
                      int crc_len, uint32_t crc_poly, int dtype);

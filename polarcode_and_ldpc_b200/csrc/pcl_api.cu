@@ -308,7 +308,7 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
     if (!(K > 0 && K < N)) return fail(PCL_EINVAL, "K must be in (0, N)");
     if (list_size < 1) return fail(PCL_EINVAL, "list_size must be >= 1");
     if (list_size > 1024) return fail(PCL_EUNSUPPORTED, "list_size %d > 1024 is not supported (one thread per list slot, one block per frame)", list_size);
-    if (N > 8192) return fail(PCL_EUNSUPPORTED, "N %d > 8192 is not supported", N);
+    if (N > 65536) return fail(PCL_EUNSUPPORTED, "N %d > 65536 is not supported (16-bit leaf positions)", N);
     if (dtype != PCL_F32 && dtype != PCL_F64) return fail(PCL_EINVAL, "bad dtype");
     if (crc_len < 0 || crc_len > 32) return fail(PCL_EINVAL, "bad crc_len");
     int n = ilog2i(N);

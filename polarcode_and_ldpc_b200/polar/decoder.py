@@ -13,7 +13,8 @@ Differences, all additive:
     has no reference behaviour to match ("parity unpinned"); with use_crc=False
     the result is the reference's.
   * list sizes up to 32 run one path per lane (a warp carries 32 / L frames); 33 .. 1024 run one
-    block per frame with a thread per slot (polar_scl_wide.cuh); N is limited to 8192 and list_size
+    block per frame with a thread per slot (polar_scl_wide.cuh); N is limited to 65536 (16-bit leaf positions; beyond 8192 as far as a
+    frame's bit arrays fit one block's shared memory: 32768 for the small lists) and list_size
     to 1024 (NotImplementedError beyond; per-leaf dumps stop at list size 256).
 There is no CPU path: constructing a decoder without a CUDA device raises.
 """

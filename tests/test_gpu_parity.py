@@ -642,7 +642,8 @@ def test_compiled_code_length_variants(NL):
 def test_large_codes():
     """Sizes beyond the BASELINE configs (benchmarks/test_code_parameters.py:33-36 goes to
     N = 4096 / n = 4032): more tree levels in the L2 scratch, more partial-sum words."""
-    for N, K, L, F in ((4096, 2048, 4, 96), (8192, 4096, 2, 40), (4096, 3000, 8, 33)):
+    for N, K, L, F in ((4096, 2048, 4, 96), (8192, 4096, 2, 40), (4096, 3000, 8, 33), (16384, 8192, 1, 24), (16384, 8192, 8, 12),
+                       (32768, 16384, 2, 8)):
         frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
         _, llr = _polar_frames(N, K, frozen, F, 1.0, N + L)
         ref = oracle.polar_scl(N, L, frozen, llr, nthreads=8)
