@@ -95,7 +95,7 @@ int pcl_polar_lp(const pcl_polar_t* h);
  * 0 = generic kernel, 1 = register-resident-bottom kernel (a lane owns a path, 32 / LP frames
  * per warp), 2 = the same with log2 N and the level split compiled in as constants, 3 = the
  * one-block-per-SM variant with the mid tree levels in tensor / shared memory, 4 = the
- * register-resident SC kernels (N = 256; N = 512 / 1024 / 2048 as 2 / 4 / 8 length-256 codes in a row), 5 = the block-per-frame kernel for list sizes 33 .. 1024
+ * register-resident SC kernels (N = 256; N = 512 … 4096 as 2 … 16 length-256 codes in a row), 5 = the block-per-frame kernel for list sizes 33 .. 1024
  * (any list_size >= 1 is what the reference accepts, src/polar/decoder.py:194-196). */
 int pcl_polar_launch_info(const pcl_polar_t* h, int* grid, int* block, int* smem_bytes, int* glevels,
                           int* fast);

@@ -480,7 +480,7 @@ static int polar_create_impl(pcl_polar_t** out, int N, int K, int list_size, con
     // (PCL_POLAR_SC1024=0: the bigger ones back on the list kernel with L = 1)
     h->sc256 = (list_size == 1 && dtype == PCL_F32 && crc_len == 0 &&
                 ((N == 256 && env_int("PCL_POLAR_SC256", 1) != 0) ||
-                 ((N == 512 || N == 1024 || N == 2048) && env_int("PCL_POLAR_SC1024", 1) != 0))) ? 1 : 0;
+                 ((N == 512 || N == 1024 || N == 2048 || N == 4096) && env_int("PCL_POLAR_SC1024", 1) != 0))) ? 1 : 0;
     if (h->TM || h->sc256) {
         if (cudaMalloc((void**)&h->d_next[0], 8) != cudaSuccess || cudaMemset(h->d_next[0], 0, 8) != cudaSuccess) {
             pcl_polar_destroy(h);
@@ -559,17 +559,18 @@ static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint
     const int NWu = h->N / 32;
     // 32 padded frame rows per warp (+ the parked partial sums of the bigger codes: 8 (M - 1) words per frame);
     // warps per block so that the SM's shared memory is used up: 2 x 3 (N = 256, 1024), 6 (N = 512), 5 (N = 2048)
-    const int wpb = (M == 2) ? 6 : (M == 8) ? 5 : PCL_SC256_WPB;
+    const int wpb = (M == 2) ? 6 : (M == 8) ? 5 : (M == 16) ? 4 : PCL_SC256_WPB;
     const int smem = wpb * 32 * (PCL_SC256_ROW + (big ? 8 * (M - 1) : 0)) * 4;
     const int bps = std::max(1, di.smem_per_sm / (smem + 1024));
     const int64_t warps_needed = (F + 31) / 32;
     const int grid = (int)std::min<int64_t>((warps_needed + wpb - 1) / wpb, (int64_t)di.sms * bps);
     h->last_grid = grid;
 #ifndef PCL_EMU
-    static bool attr_set[9] = {};
+    static bool attr_set[17] = {};
     if (!attr_set[M]) {
         const void* kern = M == 2 ? (const void*)polar_sc_big_kernel<2> : M == 4 ? (const void*)polar_sc_big_kernel<4>
-                         : M == 8 ? (const void*)polar_sc_big_kernel<8> : (const void*)polar_sc256_kernel;
+                         : M == 8 ? (const void*)polar_sc_big_kernel<8> : M == 16 ? (const void*)polar_sc_big_kernel<16>
+                         : (const void*)polar_sc256_kernel;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[M] = true;
@@ -578,6 +579,7 @@ static int polar_sc256_decode(pcl_polar* h, const void* llr_dev, int64_t F, uint
     if (M == 2) { PCL_LAUNCH(polar_sc_big_kernel<2>, grid, wpb * 32, smem, stream, P); }
     else if (M == 4) { PCL_LAUNCH(polar_sc_big_kernel<4>, grid, wpb * 32, smem, stream, P); }
     else if (M == 8) { PCL_LAUNCH(polar_sc_big_kernel<8>, grid, wpb * 32, smem, stream, P); }
+    else if (M == 16) { PCL_LAUNCH(polar_sc_big_kernel<16>, grid, wpb * 32, smem, stream, P); }
     else { PCL_LAUNCH(polar_sc256_kernel, grid, wpb * 32, smem, stream, P); }
     CUDA_TRY(cudaGetLastError());
     h->tickets[stage] += (unsigned long long)warps_needed + (unsigned long long)grid * wpb;

@@ -216,7 +216,7 @@ PCL_DEVICE void sc_bitrev256(uint32_t* X)
 }
 
 
-// ---- N = 256 M, M = 2 / 4 / 8: M length-256 codes in a row ----------------------------------------------------
+// ---- N = 256 M, M = 2 / 4 / 8 / 16: M length-256 codes in a row ----------------------------------------------------
 // The m = log2 M top levels never exist as arrays: sub-block q is a length-256 code whose channel values, in
 // reference index order, come from M CONSECUTIVE channel LLRs each through a tree of adjacent pairs -- level l
 // (1 = top) combines e[2t], e[2t+1] with f or g by bit (m - l) of q.  The partial sums g needs are the level-l
@@ -228,11 +228,11 @@ PCL_DEVICE void sc_bitrev256(uint32_t* X)
 template <int M>
 __global__ void __launch_bounds__(M == 4 ? 96 : 192) polar_sc_big_kernel(PolarScParams P)
 {
-    constexpr int m = (M == 2) ? 1 : (M == 4) ? 2 : 3;
+    constexpr int m = (M == 2) ? 1 : (M == 4) ? 2 : (M == 8) ? 3 : 4;
     constexpr int N = 256 * M;
     constexpr int PW = 8 * (M - 1);                  // parked words per frame
     constexpr int U = 32 / M;                        // lane-positions per pipeline stage (32 floats per lane)
-    static_assert(M == 2 || M == 4 || M == 8, "256 M with M = 2, 4, 8");
+    static_assert(M == 2 || M == 4 || M == 8 || M == 16, "256 M with M = 2, 4, 8, 16");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float* rows = (float*)pcl_dyn_smem() + (size_t)warp * 32 * PCL_SC256_ROW;

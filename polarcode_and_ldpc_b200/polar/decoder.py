@@ -119,7 +119,7 @@ class _PolarBase:
                                                           ctypes.byref(s), ctypes.byref(lv), ctypes.byref(fa)))
         if fa.value == 4:
             M = self.N // 256
-            wpb = {2: 6, 8: 5}.get(M, 3)
+            wpb = {2: 6, 8: 5, 16: 4}.get(M, 3)
             return {"grid": g.value, "block": 32 * wpb, "smem_bytes": wpb * 32 * (260 + (8 * (M - 1) if M > 1 else 0)) * 4, "global_levels": 0,
                     "kernel": "polar_sc256_kernel" if M == 1 else "polar_sc_big_kernel",
                     "lanes_per_path": 1, "frames_per_warp": 32, "compiled_code_length": True, "tensor_memory": False}

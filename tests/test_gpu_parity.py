@@ -230,9 +230,9 @@ def test_sc_bits_only_sizes(N, K):
     assert int((P.SCDecoder(N, K, frozen_bits=frozen).decode_batch(llr) != ref).any(axis=1).sum()) == 0
 
 
-@pytest.mark.parametrize("N,K", [(512, 256), (2048, 1024), (2048, 1500)])
+@pytest.mark.parametrize("N,K", [(512, 256), (2048, 1024), (2048, 1500), (4096, 2048)])
 def test_sc_big_kernel_other_sizes(N, K):
-    """polar_sc_big_kernel<2> / <8>: 2 and 8 length-256 codes in a row; against the oracle and the list kernel."""
+    """polar_sc_big_kernel<2> / <8> / <16>: 2, 8 and 16 length-256 codes in a row; against the oracle and the list kernel."""
     frozen = P.bhattacharyya_frozen_set(N, K, 2.0)
     _, llr = _polar_frames(N, K, frozen, 8000, 1.0, N + K)
     ref = oracle.polar_sc(N, frozen, llr, nthreads=oracle.max_threads())

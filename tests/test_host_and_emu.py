@@ -197,7 +197,8 @@ def test_emu_sc1024_register_resident_kernel():
     bits of the oracle in both lane orders, with Bhattacharyya and random frozen sets, batches that leave the last
     warp partly empty."""
     rng = np.random.default_rng(3)
-    for N, K, snr, F in ((1024, 512, 0.0, 37), (1024, 100, -2.0, 33), (512, 256, 0.0, 35), (2048, 1024, 0.5, 33), (2048, 300, -2.0, 33)):
+    for N, K, snr, F in ((1024, 512, 0.0, 37), (1024, 100, -2.0, 33), (512, 256, 0.0, 35), (2048, 1024, 0.5, 33), (2048, 300, -2.0, 33),
+                          (4096, 2048, 0.5, 33)):
         fz = P.bhattacharyya_frozen_set(N, K, 2.0) if 2 * K == N else np.sort(rng.choice(N, N - K, replace=False))
         np.random.seed(5)
         llr = P.AWGNChannel(snr).transmit_batch(P.PolarEncoder(N, K, fz).encode_batch(rng.integers(0, 2, size=(F, K))))
